@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- coded tokens/s (encode + decode) of the arithmetic-coding hot path.
+
+Workload (BASELINE.json configs[1]): coder-only sweep, precomputed random fp32 logits, vocab
+32000, 1024 streams x 2048 tokens, encode + decode on one B200.  2048 tokens x 1024 streams of
+fp32 logits are 268 GB, so the job is run as steps of [1024 streams x SLICE tokens]; one step
+= one pass of the hot path over one such batch, every stream slice coded as a self-contained
+chunk (init -> CDF lookup -> range encode -> flush -> init decoder -> fused CDF/search/decode).
+The same logits buffer (2.1 GB, far larger than the 126 MB L2) is read once by the encode
+side and once by the decode side of every step.
+
+  python bench.py --gpus N --steps K --warmup W           # this repo, device-resident `value` + host `e2e`
+  python bench.py --impl reference ...                    # the reference's CPU algorithm (oracle port)
+
+Under torchrun every rank codes its own 1024 streams (independent chunks shard with no
+data-path collective); the only collective is the gather of per-stream bit lengths.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+VOCAB = 32000
+STREAMS = 1024
+CHUNK_TOKENS = 2048
+SLICE = 16
+PREC = 48
+METRIC = "coded_tokens_per_s_enc_dec"
+UNIT = "tokens/s"
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "coder-only sweep: precomputed random fp32 logits, vocab 32000, 1024 streams x 2048 tokens, "
+                    "encode+decode",
+        "vocab": VOCAB,
+        "streams_per_gpu": STREAMS,
+        "tokens_per_stream": CHUNK_TOKENS,
+        "step": f"[{STREAMS} streams x {SLICE} tokens] slice, encode + decode, each slice a self-contained chunk "
+                f"({CHUNK_TOKENS // SLICE} steps = one full job)",
+        "prec": PREC,
+        "l2": f"inputs larger than L2: {STREAMS * SLICE * VOCAB * 4 / 1e9:.2f} GB of logits per step vs 126 MB",
+        "parallelism": f"chunk-sharded x{n_gpus}, no data-path collective",
+    }
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------ clocks sampler
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU legs (oracle; checker / baseline only)
+def cpu_sample(streams, T, seed=1):
+    rng = np.random.default_rng(seed)
+    logits = (rng.standard_normal((streams, T, VOCAB)) * 3.0).astype(np.float32)
+    syms = rng.integers(0, VOCAB, (streams, T)).astype(np.int32)
+    return logits, syms
+
+
+def cpu_baseline_leg(target_seconds=12.0):
+    """Reference algorithm (llama_compress.calc_dist + arith_code A_to_bin / A_from_bin with fudged_dist),
+    C port in oracle/, all host threads, on a bounded sample of the same workload."""
+    from oracle import oracle as orc
+    cores = orc.num_threads()
+    lg, sy = cpu_sample(cores, 2, seed=2)
+    t0 = time.perf_counter()
+    orc.ref_roundtrip_bulk(lg, sy, prec=PREC)
+    per_tok = (time.perf_counter() - t0) / 2  # one stream per core, 2 tokens each
+    T = int(max(2, min(64, target_seconds / max(per_tok, 1e-6) / 4)))
+    streams = cores * 4
+    lg, sy = cpu_sample(streams, T, seed=3)
+    t0 = time.perf_counter()
+    bad, bits = orc.ref_roundtrip_bulk(lg, sy, prec=PREC)
+    dt = time.perf_counter() - t0
+    assert bad == 0, "reference port failed to round-trip"
+    return {"value": streams * T / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{streams} streams x {T} tokens, vocab {VOCAB}, encode+decode, {dt:.1f} s; "
+                      "C port of llama_compress.calc_dist + arith_code (fudged_dist per token), pthreads",
+            "bits_per_token": bits / (streams * T)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    cores = orc.num_threads()
+    streams, T = cores * 2, 4
+    lg, sy = cpu_sample(streams, T, seed=4)
+    for _ in range(args.warmup):
+        orc.ref_roundtrip_bulk(lg, sy, prec=PREC)
+    t0 = time.perf_counter()
+    bits = 0
+    for _ in range(args.steps):
+        bad, b = orc.ref_roundtrip_bulk(lg, sy, prec=PREC)
+        assert bad == 0
+        bits += b
+    dt = time.perf_counter() - t0
+    val = streams * T * args.steps / dt
+    sample = f"each step {streams} streams x {T} tokens, vocab {VOCAB}, encode+decode (bounded sample of the workload)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32/f64/bigint", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "bits_per_token": bits / (streams * T * args.steps), "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------ GPU legs
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from lac_b200 import _ffi
+    L = _ffi.lib()  # raises if the CUDA library is missing: there is no fallback
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    S, T, V = STREAMS, SLICE, VOCAB
+    rows = S * T
+    cap = T * 8 + 64
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    logits = torch.randn((S, T, V), generator=gen, device=dev) * 3.0
+    # symbols drawn from the model distribution (what an LLM coder sees on in-distribution text)
+    syms = torch.multinomial(torch.softmax(logits.view(rows, V), -1), 1, generator=gen).view(S, T).to(torch.int32)
+    pairs = torch.empty((rows, 2), dtype=torch.int32, device=dev)
+    enc_state = torch.zeros((S, _ffi.ENC_STATE_BYTES), dtype=torch.uint8, device=dev)
+    dec_state = torch.zeros((S, _ffi.DEC_STATE_BYTES), dtype=torch.uint8, device=dev)
+    out = torch.zeros((S, cap), dtype=torch.uint8, device=dev)
+    offsets = (torch.arange(S + 1, device=dev, dtype=torch.int64) * cap)
+    back = torch.zeros((S, T), dtype=torch.int32, device=dev)
+    gathered = torch.zeros((world, S), dtype=torch.int64, device=dev) if world > 1 else None
+    stream = torch.cuda.current_stream().cuda_stream
+    ck = _ffi.check
+
+    def step(ev=None):
+        # encode side: fused softmax -> quantise -> clamp -> prefix sums -> (lo, hi), then the range coder
+        ck(L.lac_enc_init(enc_state.data_ptr(), S, PREC, stream))
+        if ev: ev[0].record()
+        ck(L.lac_cdf_lookup_f32(logits.data_ptr(), rows, V, V, syms.data_ptr(), pairs.data_ptr(), None, stream))
+        if ev: ev[1].record()
+        ck(L.lac_ac_encode_pairs(pairs.data_ptr(), S, T, T, 1, None, enc_state.data_ptr(), out.data_ptr(), cap, 1,
+                                 PREC, stream))
+        if ev: ev[2].record()
+        # decode side: rebuild the CDF from the same logits, search, narrow, renormalise
+        ck(L.lac_dec_init(dec_state.data_ptr(), S, PREC, out.data_ptr(), offsets.data_ptr(), stream))
+        ck(L.lac_ac_decode_logits_f32(logits.data_ptr(), S, T, T * V, V, V, None, dec_state.data_ptr(),
+                                      out.data_ptr(), offsets.data_ptr(), back.data_ptr(), T, PREC, stream))
+        if ev: ev[3].record()
+        if world > 1:  # the one collective: per-stream bit lengths for the container index
+            nb = enc_state.view(torch.int64).view(S, 4)[:, 2].contiguous()
+            dist.all_gather_into_tensor(gathered.view(-1), nb)
+    launches_per_step = 5
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    assert torch.equal(back, syms), "round trip failed"
+    nbits = enc_state.view(torch.int64).view(S, 4)[:, 2]
+    bits_per_token = float(nbits.sum().item()) / rows
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_beg.record()
+    for k in range(args.steps):
+        step(evs[k])
+    t_end.record()
+    barrier()
+    elapsed_ms = t_beg.elapsed_time(t_end)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    assert torch.equal(back, syms), "round trip failed in the timed region"
+    lookup_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
+    coder_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+    decode_ms = statistics.mean(e[2].elapsed_time(e[3]) for e in evs)
+
+    # ---------------- e2e: HOST buffers through the C ABI, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e_steps = max(2, min(args.steps, args.e2e_steps))
+        h_logits = torch.empty((S, T, V), dtype=torch.float32).pin_memory()
+        h_logits.copy_(logits)
+        h_syms = syms.cpu().pin_memory()
+        h_out = torch.zeros((S, cap), dtype=torch.uint8).pin_memory()
+        h_nbits = torch.zeros(S, dtype=torch.int64).pin_memory()
+        h_back = torch.zeros((S, T), dtype=torch.int32).pin_memory()
+        h_offs = (torch.arange(S + 1, dtype=torch.int64) * cap)
+
+        def host_step():
+            ck(L.lac_encode_logits_host(h_logits.data_ptr(), h_syms.data_ptr(), S, T, V, h_out.data_ptr(), cap,
+                                        h_nbits.data_ptr(), PREC))
+            ck(L.lac_decode_logits_host(h_logits.data_ptr(), S, T, V, h_out.data_ptr(), h_offs.data_ptr(),
+                                        h_back.data_ptr(), PREC))
+        host_step()
+        assert torch.equal(h_back, h_syms), "host-API round trip failed"
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            host_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = 2 * rows * V * 4 + rows * 4 + S * cap + (S + 1) * 8
+        d2h = S * cap + S * _ffi.ENC_STATE_BYTES + rows * 4
+        e2e = {"value": world * rows * e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": e_steps, "ms_per_step": dt / e_steps * 1e3,
+               "api": "lac_encode_logits_host + lac_decode_logits_host (pinned host logits in, host bytes/symbols out)"}
+    clk = clocks.stop() if rank == 0 else None
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg_bytes = rows * (V * 4 + 4 + 8)
+        look_gbs = alg_bytes / (lookup_ms * 1e-3) / 1e9
+        dec_gbs = rows * (V * 4 + 4) / (decode_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": world * rows * args.steps / (elapsed_ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32->u32/u64", "data": "synthetic", "config": workload_config(world),
+            "roofline": {"bound": "hbm", "kernel": "lookup_kernel<4> (fused softmax->quantise->clamp->prefix-sum CDF lookup)",
+                         "achieved": look_gbs, "peak": peak, "unit": "GB/s", "frac": look_gbs / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "ms_per_launch": lookup_ms,
+                         "decode_kernel": {"achieved": dec_gbs, "frac": dec_gbs / peak, "ms_per_launch": decode_ms},
+                         "coder_kernel_ms": coder_ms},
+            "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clk,
+            "bits_per_token": bits_per_token,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_leg()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="lac_b200", choices=["lac_b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,292 @@
+"""Batched GPU coder API: torch tensors in, torch tensors / bytes out, every operation a call
+into liblac_b200.so through the C ABI (lac_b200/_ffi.py).  torch is used for device memory
+and streams only.
+
+Conventions
+-----------
+* uint32 values (LQ32 cumulative frequencies, pairs) are carried in torch.int32 tensors
+  holding the same 32 bits; `u32(t)` widens them to int64 for arithmetic on the host side.
+* Bitstreams are MSB-first bytes, byte-for-byte what the reference's
+  bytes(group_bits(A_to_bin.bits(...))) (arith_code.py:347-358) / packbits
+  (arithmetic_coding.py:200-214) produce.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _ffi
+from ._ffi import LacError, check, lib
+
+DEFAULT_PREC = 48  # llama_compress.py:4 r(..., prec=48)
+
+
+def _cur_stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(t: torch.Tensor, name: str, dtype=None):
+    if not t.is_cuda:
+        raise LacError(_ffi.LAC_E_ARG, f"{name} must be a CUDA tensor (lac_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise LacError(_ffi.LAC_E_ARG, f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise LacError(_ffi.LAC_E_ARG, f"{name} must be contiguous")
+
+
+def u32(t: torch.Tensor) -> torch.Tensor:
+    """int32-carried uint32 -> int64 values."""
+    return t.to(torch.int64) & 0xFFFFFFFF
+
+
+# ------------------------------------------------------------------------------------ (a) CDF
+def cdf_build(logits: torch.Tensor) -> torch.Tensor:
+    """LQ32 exclusive cumulative table per row: int32-carried uint32 [rows, V]; total 2^32 implicit.
+
+    Replaces Llama_AC.calc_dist (llama_compress.py:24-30) / ProbPredictor.calc_dist
+    (arith_code.py:120-126)."""
+    _need_cuda(logits, "logits", torch.float32)
+    rows, V = logits.shape
+    cum = torch.empty((rows, V), dtype=torch.int32, device=logits.device)
+    check(lib().lac_cdf_build_f32(logits.data_ptr(), rows, V, V, cum.data_ptr(), _cur_stream()))
+    return cum
+
+
+def cdf_lookup(logits: torch.Tensor, syms: torch.Tensor, status: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(cum[sym], cum[sym+1]) per row, int32-carried uint32 [rows, 2]; hi == 0 means 2^32."""
+    _need_cuda(logits, "logits", torch.float32)
+    _need_cuda(syms, "syms", torch.int32)
+    rows, V = logits.shape
+    if syms.numel() != rows:
+        raise LacError(_ffi.LAC_E_ARG, "syms must have one entry per logits row")
+    pairs = torch.empty((rows, 2), dtype=torch.int32, device=logits.device)
+    check(lib().lac_cdf_lookup_f32(logits.data_ptr(), rows, V, V, syms.data_ptr(), pairs.data_ptr(),
+                                   status.data_ptr() if status is not None else None, _cur_stream()))
+    return pairs
+
+
+def cdf_to_dist(cum: torch.Tensor) -> np.ndarray:
+    """Exclusive uint32 table(s) -> int64 inclusive cumulative tables as CDFPredictor.dist holds them."""
+    c = u32(cum).cpu().numpy()
+    out = np.empty_like(c)
+    out[..., :-1] = c[..., 1:]
+    out[..., -1] = 1 << 32
+    return out
+
+
+# ------------------------------------------------------------------------------------ (b) coder
+def _collect_streams(out: torch.Tensor, state: torch.Tensor) -> Tuple[List[bytes], np.ndarray]:
+    st = state.cpu().numpy().view(np.uint8).reshape(-1, _ffi.ENC_STATE_BYTES)
+    nbits = st[:, 16:24].copy().view(np.uint64).reshape(-1)
+    status = st[:, 24:28].copy().view(np.uint32).reshape(-1)
+    if (status & _ffi.LAC_ST_CAP).any():
+        raise LacError(_ffi.LAC_E_CAP, f"output capacity exceeded on streams {np.nonzero(status & 1)[0][:8].tolist()}")
+    if (status & _ffi.LAC_ST_SYMBOL).any():
+        raise LacError(_ffi.LAC_E_SYMBOL, f"symbol out of range on streams {np.nonzero(status & 2)[0][:8].tolist()}")
+    if (status & _ffi.LAC_ST_TABLE).any():
+        raise LacError(_ffi.LAC_E_ARG, f"unusable table (zero-width symbol) on streams {np.nonzero(status & 4)[0][:8].tolist()}")
+    host = out.cpu().numpy()
+    nbytes = (nbits + 7) // 8
+    return [host[i, : int(nbytes[i])].tobytes() for i in range(host.shape[0])], nbits
+
+
+class StreamEncoder:
+    """n_streams independent A_to_bin coders (arith_code.py:147-231) living on the GPU.
+
+    Feed tokens in slices (state persists between calls), then finish()."""
+
+    def __init__(self, n_streams: int, prec: int = DEFAULT_PREC, capacity_bytes: int = 1 << 16, device="cuda"):
+        self.n, self.prec, self.cap = int(n_streams), int(prec), int(capacity_bytes)
+        self.device = torch.device(device)
+        self.state = torch.zeros((self.n, _ffi.ENC_STATE_BYTES), dtype=torch.uint8, device=self.device)
+        self.out = torch.zeros((self.n, self.cap), dtype=torch.uint8, device=self.device)
+        check(lib().lac_enc_init(self.state.data_ptr(), self.n, self.prec, _cur_stream()))
+        self.finished = False
+
+    def _ntok(self, ntok):
+        if ntok is None:
+            return None
+        _need_cuda(ntok, "ntok", torch.int32)
+        return ntok.data_ptr()
+
+    def encode_pairs(self, pairs: torch.Tensor, ntok: Optional[torch.Tensor] = None, finish: bool = False):
+        """pairs: int32-carried uint32 [n_streams, T, 2] from cdf_lookup."""
+        _need_cuda(pairs, "pairs", torch.int32)
+        S, T, two = pairs.shape
+        if S != self.n or two != 2:
+            raise LacError(_ffi.LAC_E_ARG, "pairs must be [n_streams, T, 2]")
+        check(lib().lac_ac_encode_pairs(pairs.data_ptr(), S, T, T, 1, self._ntok(ntok), self.state.data_ptr(),
+                                        self.out.data_ptr(), self.cap, int(finish), self.prec, _cur_stream()))
+        self.finished = self.finished or finish
+
+    def encode_logits(self, logits: torch.Tensor, syms: torch.Tensor, ntok: Optional[torch.Tensor] = None,
+                      finish: bool = False):
+        """logits [n_streams, T, V] fp32, syms [n_streams, T] int32: fused CDF lookup, then the coder."""
+        S, T, V = logits.shape
+        pairs = cdf_lookup(logits.reshape(S * T, V), syms.reshape(S * T))
+        self.encode_pairs(pairs.view(S, T, 2), ntok, finish)
+
+    def encode_tables(self, dist: torch.Tensor, syms: torch.Tensor, minp: torch.Tensor,
+                      ntok: Optional[torch.Tensor] = None, finish: bool = False, wrap64: bool = False):
+        """General int64 inclusive cumulative tables (CDFPredictor.dist): [V] shared, [T, V] per position,
+        or [n_streams, T, V].  minp: matching [1] / [T] / [n_streams, T] int64 (predictor.minp)."""
+        _need_cuda(dist, "dist", torch.int64)
+        _need_cuda(minp, "minp", torch.int64)
+        _need_cuda(syms, "syms", torch.int32)
+        S, T = syms.shape
+        V, ss, ts, mss, mts = _table_strides(dist, minp, S, T)
+        check(lib().lac_ac_encode_tables(dist.data_ptr(), V, ss, ts, minp.data_ptr(), mss, mts, syms.data_ptr(), S, T,
+                                         self._ntok(ntok), self.state.data_ptr(), self.out.data_ptr(), self.cap,
+                                         int(finish), self.prec, _ffi.LAC_F_WRAP64 if wrap64 else 0, _cur_stream()))
+        self.finished = self.finished or finish
+
+    def acs_encode_tables(self, cdf: torch.Tensor, syms: torch.Tensor, ntok: Optional[torch.Tensor] = None,
+                          finish: bool = False):
+        """ACSampler semantics (arithmetic_coding.py:73-93): int64-carried uint64 inclusive tables."""
+        _need_cuda(cdf, "cdf", torch.int64)
+        _need_cuda(syms, "syms", torch.int32)
+        S, T = syms.shape
+        V, ss, ts, _, _ = _table_strides(cdf, None, S, T)
+        check(lib().lac_acs_encode_tables(cdf.data_ptr(), V, ss, ts, syms.data_ptr(), S, T, self._ntok(ntok),
+                                          self.state.data_ptr(), self.out.data_ptr(), self.cap, int(finish),
+                                          self.prec, _cur_stream()))
+        self.finished = self.finished or finish
+
+    def finish(self):
+        if not self.finished:
+            empty = torch.empty((self.n, 0, 2), dtype=torch.int32, device=self.device)
+            if self.prec >= 34:
+                self.encode_pairs(empty, finish=True)
+            else:  # pairs entry point needs prec >= 34; an empty table call flushes any precision
+                dist = torch.ones(1, dtype=torch.int64, device=self.device)
+                syms = torch.empty((self.n, 0), dtype=torch.int32, device=self.device)
+                self.encode_tables(dist, syms, dist, finish=True)
+
+    def nbits(self) -> np.ndarray:
+        st = self.state.cpu().numpy().view(np.uint8).reshape(-1, _ffi.ENC_STATE_BYTES)
+        return st[:, 16:24].copy().view(np.uint64).reshape(-1)
+
+    def bitstreams(self) -> Tuple[List[bytes], np.ndarray]:
+        """(bytes per stream, bit length per stream); raises on capacity / symbol errors."""
+        return _collect_streams(self.out, self.state)
+
+
+def _table_strides(tab: torch.Tensor, minp: Optional[torch.Tensor], S: int, T: int):
+    if tab.dim() == 1:
+        V, ss, ts, mss, mts = tab.shape[0], 0, 0, 0, 0
+    elif tab.dim() == 2:
+        if tab.shape[0] < T:
+            raise LacError(_ffi.LAC_E_ARG, "per-position tables need at least T rows")
+        V, ss, ts, mss, mts = tab.shape[1], 0, tab.shape[1], 0, 1
+    elif tab.dim() == 3:
+        if tab.shape[0] != S or tab.shape[1] < T:
+            raise LacError(_ffi.LAC_E_ARG, "tables must be [n_streams, >=T, V]")
+        V, ss, ts, mss, mts = tab.shape[2], tab.shape[1] * tab.shape[2], tab.shape[2], tab.shape[1], 1
+    else:
+        raise LacError(_ffi.LAC_E_ARG, "tables must be 1-, 2- or 3-dimensional")
+    if minp is not None:
+        need = 1 if tab.dim() == 1 else (tab.shape[0] if tab.dim() == 2 else tab.shape[0] * tab.shape[1])
+        if minp.numel() != need:
+            raise LacError(_ffi.LAC_E_ARG, f"minp needs {need} entries, got {minp.numel()}")
+    return V, ss, ts, mss, mts
+
+
+def pack_streams(streams: Sequence[bytes], device="cuda") -> Tuple[torch.Tensor, torch.Tensor]:
+    """Concatenate bitstreams into one device buffer + int64 offsets [n + 1] (padded so reads stay in bounds)."""
+    offs = np.zeros(len(streams) + 1, dtype=np.int64)
+    for i, s in enumerate(streams):
+        offs[i + 1] = offs[i] + len(s)
+    buf = np.frombuffer(b"".join(streams) + b"\0" * 16, dtype=np.uint8).copy()
+    return torch.from_numpy(buf).to(device), torch.from_numpy(offs).to(device)
+
+
+class StreamDecoder:
+    """n_streams independent A_from_bin decoders (arith_code.py:233-345) on the GPU, decoding a
+    known number of tokens (the reference has no length framing; the container supplies it)."""
+
+    def __init__(self, streams: Sequence[bytes], prec: int = DEFAULT_PREC, device="cuda"):
+        self.n, self.prec = len(streams), int(prec)
+        self.device = torch.device(device)
+        self.bytes, self.offsets = pack_streams(streams, self.device)
+        self.state = torch.zeros((self.n, _ffi.DEC_STATE_BYTES), dtype=torch.uint8, device=self.device)
+        check(lib().lac_dec_init(self.state.data_ptr(), self.n, self.prec, self.bytes.data_ptr(),
+                                 self.offsets.data_ptr(), _cur_stream()))
+
+    def decode_logits(self, logits: torch.Tensor, ntok: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """logits [n_streams, T, V] fp32 -> symbols int32 [n_streams, T] (fused CDF rebuild + search + update)."""
+        _need_cuda(logits, "logits", torch.float32)
+        S, T, V = logits.shape
+        if S != self.n:
+            raise LacError(_ffi.LAC_E_ARG, "logits must be [n_streams, T, V]")
+        syms = torch.zeros((S, T), dtype=torch.int32, device=self.device)
+        check(lib().lac_ac_decode_logits_f32(logits.data_ptr(), S, T, T * V, V, V,
+                                             ntok.data_ptr() if ntok is not None else None, self.state.data_ptr(),
+                                             self.bytes.data_ptr(), self.offsets.data_ptr(), syms.data_ptr(), T,
+                                             self.prec, _cur_stream()))
+        return syms
+
+    def decode_step(self, logits: torch.Tensor) -> torch.Tensor:
+        """One model-in-the-loop step: logits [n_streams, V] -> symbols [n_streams]."""
+        return self.decode_logits(logits.unsqueeze(1)).squeeze(1)
+
+    def decode_tables(self, dist: torch.Tensor, minp: torch.Tensor, T: int, ntok: Optional[torch.Tensor] = None,
+                      wrap64: bool = False) -> torch.Tensor:
+        _need_cuda(dist, "dist", torch.int64)
+        _need_cuda(minp, "minp", torch.int64)
+        V, ss, ts, mss, mts = _table_strides(dist, minp, self.n, T)
+        syms = torch.zeros((self.n, T), dtype=torch.int32, device=self.device)
+        check(lib().lac_ac_decode_tables(dist.data_ptr(), V, ss, ts, minp.data_ptr(), mss, mts, self.n, T,
+                                         ntok.data_ptr() if ntok is not None else None, self.state.data_ptr(),
+                                         self.bytes.data_ptr(), self.offsets.data_ptr(), syms.data_ptr(), T,
+                                         self.prec, _ffi.LAC_F_WRAP64 if wrap64 else 0, _cur_stream()))
+        self._check_status()
+        return syms
+
+    def acs_decode_tables(self, cdf: torch.Tensor, T: int, ntok: Optional[torch.Tensor] = None) -> torch.Tensor:
+        _need_cuda(cdf, "cdf", torch.int64)
+        V, ss, ts, _, _ = _table_strides(cdf, None, self.n, T)
+        syms = torch.zeros((self.n, T), dtype=torch.int32, device=self.device)
+        check(lib().lac_acs_decode_tables(cdf.data_ptr(), V, ss, ts, self.n, T,
+                                          ntok.data_ptr() if ntok is not None else None, self.state.data_ptr(),
+                                          self.bytes.data_ptr(), self.offsets.data_ptr(), syms.data_ptr(), T,
+                                          self.prec, _cur_stream()))
+        self._check_status()
+        return syms
+
+    def _check_status(self):
+        st = self.state.cpu().numpy().view(np.uint8).reshape(-1, _ffi.DEC_STATE_BYTES)
+        status = st[:, 32:36].copy().view(np.uint32).reshape(-1)
+        if status.any():
+            raise LacError(_ffi.LAC_E_ARG, f"unusable table on streams {np.nonzero(status)[0][:8].tolist()}")
+
+
+# ------------------------------------------------------------------------------------ host-buffer calls
+def encode_logits_host(logits: np.ndarray, syms: np.ndarray, prec: int = DEFAULT_PREC,
+                       capacity_bytes: Optional[int] = None, out: Optional[np.ndarray] = None):
+    """HOST numpy buffers in, HOST buffers out (copies inside): what bench.py's e2e leg times.
+    Returns (out [n_streams, capacity] uint8, nbits [n_streams] uint64)."""
+    logits = np.ascontiguousarray(logits, dtype=np.float32)
+    syms = np.ascontiguousarray(syms, dtype=np.int32)
+    S, T, V = logits.shape
+    cap = int(capacity_bytes or (T * 8 + 64))
+    if out is None:
+        out = np.zeros((S, cap), dtype=np.uint8)
+    nbits = np.zeros(S, dtype=np.uint64)
+    check(lib().lac_encode_logits_host(logits.ctypes.data, syms.ctypes.data, S, T, V, out.ctypes.data, cap,
+                                       nbits.ctypes.data, prec))
+    return out, nbits
+
+
+def decode_logits_host(logits: np.ndarray, data: np.ndarray, offsets: np.ndarray, prec: int = DEFAULT_PREC,
+                       out: Optional[np.ndarray] = None) -> np.ndarray:
+    logits = np.ascontiguousarray(logits, dtype=np.float32)
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    S, T, V = logits.shape
+    if out is None:
+        out = np.zeros((S, T), dtype=np.int32)
+    check(lib().lac_decode_logits_host(logits.ctypes.data, S, T, V, data.ctypes.data, offsets.ctypes.data,
+                                       out.ctypes.data, prec))
+    return out

@@ -1,0 +1,338 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI,
+against the CPU oracle and the golden vectors generated from the real reference.
+Bar: bit-exact everywhere (integer / byte / index work)."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():  # collected on CPU boxes, deselected by -m "not gpu"
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from lac_b200 import _ffi, coder  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _special_rows(V, rng):
+    rows = [
+        rng.standard_normal(V) * 1.0,
+        rng.standard_normal(V) * 8.0,
+        rng.standard_normal(V) * 30.0,
+        np.zeros(V),
+        np.full(V, -1e30),
+        np.full(V, 3e38),
+        rng.standard_normal(V) * 1e-30,
+        np.linspace(-200, 50, V),
+        -np.abs(rng.standard_normal(V)) * 100,
+    ]
+    a = rng.standard_normal(V) * 5
+    a[rng.integers(0, V, max(1, V // 7))] = -np.inf
+    rows.append(a)
+    b = rng.standard_normal(V) * 5
+    b[rng.integers(0, V)] = np.nan
+    rows.append(b)
+    c = rng.standard_normal(V)
+    c[rng.integers(0, V)] = np.inf
+    rows.append(c)
+    rows.append(np.full(V, -np.inf))
+    rows.append(np.full(V, np.nan))
+    d = np.full(V, -np.inf)
+    d[rng.integers(0, V)] = 2.5
+    rows.append(d)
+    return np.stack(rows).astype(np.float32)
+
+
+@pytest.mark.parametrize("V", [1, 2, 3, 4, 5, 31, 32, 33, 100, 128, 257, 1000, 4096, 8191, 32000, 32768])
+def test_cdf_build_bit_exact(V):
+    rng = np.random.default_rng(V)
+    logits = _special_rows(V, rng)
+    want = orc.lq32_cdf(logits)
+    got = coder.cdf_build(_dev(logits)).cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, want)
+    # every frequency >= 1 and the implicit total is 2^32
+    full = np.concatenate([want.astype(np.int64), np.full((len(want), 1), 1 << 32)], axis=1)
+    assert (np.diff(full, axis=1) >= 1).all()
+
+
+def test_cdf_build_unaligned_rows_use_scalar_path():
+    rng = np.random.default_rng(5)
+    V = 1001  # odd vocab: rows are not 16-byte aligned
+    logits = (rng.standard_normal((37, V)) * 4).astype(np.float32)
+    got = coder.cdf_build(_dev(logits)).cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, orc.lq32_cdf(logits))
+
+
+@pytest.mark.parametrize("V", [2, 7, 128, 1001, 32000])
+def test_cdf_lookup_bit_exact(V):
+    rng = np.random.default_rng(100 + V)
+    rows = 300 if V < 5000 else 64
+    logits = (rng.standard_normal((rows, V)) * rng.choice([0.5, 3.0, 12.0], (rows, 1))).astype(np.float32)
+    syms = rng.integers(0, V, rows).astype(np.int32)
+    syms[:4] = [0, V - 1, V // 2, max(0, V - 2)]
+    lo, hi = orc.lq32_lookup(logits, syms)
+    pairs = coder.cdf_lookup(_dev(logits), _dev(syms)).cpu().numpy().view(np.uint32)
+    assert np.array_equal(pairs[:, 0], lo)
+    assert np.array_equal(pairs[:, 1].astype(np.uint64), hi & 0xFFFFFFFF)  # 2^32 is carried as 0
+    assert (hi[syms == V - 1] == (1 << 32)).all()
+
+
+def test_cdf_lookup_flags_bad_symbols():
+    V = 64
+    logits = _dev(np.zeros((3, V), dtype=np.float32))
+    syms = _dev(np.array([5, -1, V], dtype=np.int32))
+    status = torch.zeros(3, dtype=torch.int32, device="cuda")
+    coder.cdf_lookup(logits, syms, status)
+    assert status.cpu().tolist() == [0, _ffi.LAC_ST_SYMBOL, _ffi.LAC_ST_SYMBOL]
+
+
+def _oracle_stream(logits_s, syms_s, prec):
+    lo, hi = orc.lq32_lookup(logits_s, syms_s)
+    return orc.pack_bits(orc.ac_encode_pairs(lo, hi, prec=prec)).tobytes()
+
+
+@pytest.mark.parametrize("prec", [34, 40, 48, 56, 60])
+def test_encode_decode_logits_vs_oracle_and_reference_semantics(prec):
+    rng = np.random.default_rng(prec)
+    S, T, V = 9, 40, 300
+    logits = (rng.standard_normal((S, T, V)) * rng.choice([1.0, 6.0, 20.0], (S, 1, 1))).astype(np.float32)
+    syms = np.empty((S, T), dtype=np.int32)
+    for s in range(S):
+        for t in range(T):
+            p = np.exp((logits[s, t] - logits[s, t].max()).astype(np.float64))
+            syms[s, t] = rng.choice(V, p=p / p.sum()) if rng.random() < 0.7 else rng.integers(0, V)
+    enc = coder.StreamEncoder(S, prec=prec, capacity_bytes=T * 8 + 64)
+    enc.encode_logits(_dev(logits), _dev(syms), finish=True)
+    streams, nbits = enc.bitstreams()
+    for s in range(S):
+        assert streams[s] == _oracle_stream(logits[s], syms[s], prec)
+        # level-1 parity: the REFERENCE coder (A_to_bin + CDFPredictor restated literally) fed the
+        # same integer tables yields the same bits
+        dist = orc.lq32_to_dist(orc.lq32_cdf(logits[s]))
+        ref_bits = orc.ac_encode(dist, syms[s], prec=prec, stop=1, minp=np.ones(T, dtype=np.int64))
+        assert len(ref_bits) == nbits[s]
+        assert orc.pack_bits(ref_bits).tobytes() == streams[s]
+        # and the literal reference decoder returns our symbols first
+        dec, rc = orc.ac_decode(dist, ref_bits, prec=prec, stop=0, minp=np.ones(T, dtype=np.int64), max_syms=T)
+        assert rc == 0 and np.array_equal(dec[:T], syms[s])
+    back = coder.StreamDecoder(streams, prec=prec).decode_logits(_dev(logits)).cpu().numpy()
+    assert np.array_equal(back, syms)
+
+
+def test_encode_in_slices_and_ragged_matches_one_shot():
+    rng = np.random.default_rng(1)
+    S, T, V = 33, 64, 128
+    logits = (rng.standard_normal((S, T, V)) * 4).astype(np.float32)
+    syms = rng.integers(0, V, (S, T)).astype(np.int32)
+    ntok = rng.integers(0, T + 1, S).astype(np.int32)
+    ntok[:3] = [0, 1, T]
+    dl, ds = _dev(logits), _dev(syms)
+    one = coder.StreamEncoder(S, capacity_bytes=T * 8 + 64)
+    one.encode_logits(dl, ds, ntok=_dev(ntok), finish=True)
+    a, abits = one.bitstreams()
+    # same thing in 4 slices of 16 tokens with per-slice ragged counts
+    sl = coder.StreamEncoder(S, capacity_bytes=T * 8 + 64)
+    for k in range(4):
+        part = np.clip(ntok - 16 * k, 0, 16).astype(np.int32)
+        sl.encode_logits(dl[:, 16 * k:16 * k + 16].contiguous(), ds[:, 16 * k:16 * k + 16].contiguous(), ntok=_dev(part))
+    sl.finish()
+    b, bbits = sl.bitstreams()
+    assert a == b and np.array_equal(abits, bbits)
+    for s in range(S):
+        assert a[s] == _oracle_stream(logits[s, :ntok[s]], syms[s, :ntok[s]], 48)
+    dec = coder.StreamDecoder(a).decode_logits(dl, ntok=_dev(ntok)).cpu().numpy()
+    for s in range(S):
+        assert np.array_equal(dec[s, :ntok[s]], syms[s, :ntok[s]])
+
+
+def test_decode_step_by_step_matches_bulk():
+    rng = np.random.default_rng(2)
+    S, T, V = 20, 24, 1000
+    logits = (rng.standard_normal((S, T, V)) * 5).astype(np.float32)
+    syms = rng.integers(0, V, (S, T)).astype(np.int32)
+    dl = _dev(logits)
+    enc = coder.StreamEncoder(S, capacity_bytes=T * 8 + 64)
+    enc.encode_logits(dl, _dev(syms), finish=True)
+    streams, _ = enc.bitstreams()
+    dec = coder.StreamDecoder(streams)
+    out = torch.stack([dec.decode_step(dl[:, t].contiguous()) for t in range(T)], dim=1).cpu().numpy()
+    assert np.array_equal(out, syms)
+
+
+def test_peaked_distributions_and_rare_symbols_roundtrip():
+    """Very confident rows with the coded symbol deep in the tail: long renormalisations, carries."""
+    rng = np.random.default_rng(3)
+    S, T, V = 16, 50, 4096
+    logits = (rng.standard_normal((S, T, V))).astype(np.float32)
+    hot = rng.integers(0, V, (S, T))
+    np.put_along_axis(logits, hot[..., None], 60.0, axis=2)
+    syms = np.where(rng.random((S, T)) < 0.5, hot, rng.integers(0, V, (S, T))).astype(np.int32)
+    dl = _dev(logits)
+    enc = coder.StreamEncoder(S, capacity_bytes=T * 8 + 64)
+    enc.encode_logits(dl, _dev(syms), finish=True)
+    streams, _ = enc.bitstreams()
+    for s in range(S):
+        assert streams[s] == _oracle_stream(logits[s], syms[s], 48)
+    assert np.array_equal(coder.StreamDecoder(streams).decode_logits(dl).cpu().numpy(), syms)
+
+
+def test_capacity_overflow_is_reported():
+    rng = np.random.default_rng(4)
+    S, T, V = 2, 64, 256
+    logits = _dev((rng.standard_normal((S, T, V))).astype(np.float32))
+    syms = _dev(rng.integers(0, V, (S, T)).astype(np.int32))
+    enc = coder.StreamEncoder(S, capacity_bytes=8)
+    enc.encode_logits(logits, syms, finish=True)
+    with pytest.raises(_ffi.LacError) as e:
+        enc.bitstreams()
+    assert e.value.code == _ffi.LAC_E_CAP
+
+
+# ------------------------------------------------------------------ golden vectors of the real reference
+def _golden(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def test_golden_ac_small_tables(golden_dir):
+    g = _golden(golden_dir, "ac_small.npz")
+    n_checked = n_dec = 0
+    for nm in g["names"]:
+        prec, stop = int(g[f"{nm}/prec"]), int(g[f"{nm}/stop"])
+        dist, syms = g[f"{nm}/dist"], g[f"{nm}/syms"].astype(np.int32)
+        minp = np.array([int(g[f"{nm}/minp"])], dtype=np.int64)
+        T = len(syms)
+        enc = coder.StreamEncoder(1, prec=prec, capacity_bytes=T * 8 + 64)
+        enc.encode_tables(_dev(dist), _dev(syms[None]), _dev(minp), finish=bool(stop))
+        streams, nbits = enc.bitstreams()
+        want = g[f"{nm}/bits"]
+        assert nbits[0] == len(want), nm
+        assert streams[0] == orc.pack_bits(want).tobytes(), nm
+        n_checked += 1
+        # decode: first T symbols of the reference decoder's own output
+        if str(g[f"{nm}/dec_err"]) == "" and len(g[f"{nm}/dec"]) >= T and T > 0:
+            assert np.array_equal(g[f"{nm}/dec"][:T], syms)  # the reference round-trips here
+            dec = coder.StreamDecoder([orc.pack_bits(want).tobytes()], prec=prec)
+            out = dec.decode_tables(_dev(dist), _dev(minp), T).cpu().numpy()[0]
+            assert np.array_equal(out, syms), nm
+            n_dec += 1
+    assert n_checked > 500 and n_dec > 200
+
+
+def test_golden_ac_llama_wrap64(golden_dir):
+    g = _golden(golden_dir, "ac_llama.npz")
+    for nm in g["names"]:
+        tabs, minp, syms = g[f"{nm}/tables"], g[f"{nm}/minp"], g[f"{nm}/syms"].astype(np.int32)
+        T = len(syms)
+        enc = coder.StreamEncoder(1, prec=48, capacity_bytes=T * 8 + 64)
+        enc.encode_tables(_dev(tabs), _dev(syms[None]), _dev(minp), finish=True, wrap64=True)
+        streams, nbits = enc.bitstreams()
+        assert nbits[0] == len(g[f"{nm}/bits"])
+        assert streams[0] == orc.pack_bits(g[f"{nm}/bits"]).tobytes()
+        out = coder.StreamDecoder(streams, prec=48).decode_tables(_dev(tabs), _dev(minp), T, wrap64=True)
+        assert np.array_equal(out.cpu().numpy()[0], syms)
+        # exact-integer semantics (what CDFPredictor does with Python ints) also round-trips and
+        # matches the oracle's exact mode
+        enc2 = coder.StreamEncoder(1, prec=48, capacity_bytes=T * 8 + 64)
+        enc2.encode_tables(_dev(tabs), _dev(syms[None]), _dev(minp), finish=True)
+        s2, _ = enc2.bitstreams()
+        assert s2[0] == orc.pack_bits(orc.ac_encode(tabs, syms, prec=48, minp=minp)).tobytes()
+        out2 = coder.StreamDecoder(s2, prec=48).decode_tables(_dev(tabs), _dev(minp), T)
+        assert np.array_equal(out2.cpu().numpy()[0], syms)
+
+
+def _adaptive_tables(data, V=256):
+    counts = np.ones(V, dtype=np.int64)
+    tabs = np.empty((len(data), V), dtype=np.int64)
+    for i, b in enumerate(data):
+        tabs[i] = np.cumsum(counts)
+        counts[b] += 1
+    return tabs
+
+
+def test_golden_ac_adaptive_16k(golden_dir):
+    g = _golden(golden_dir, "ac_adaptive.npz")
+    data = g["data"]
+    T, prec = len(data), int(g["prec"])
+    tabs = _dev(_adaptive_tables(data))
+    minp = torch.ones(T, dtype=torch.int64, device="cuda")
+    enc = coder.StreamEncoder(1, prec=prec, capacity_bytes=T * 2)
+    enc.encode_tables(tabs, _dev(data.astype(np.int32)[None]), minp, finish=True)
+    streams, _ = enc.bitstreams()
+    assert streams[0] == g["comp"].tobytes()
+    out = coder.StreamDecoder(streams, prec=prec).decode_tables(tabs, minp, T).cpu().numpy()[0]
+    assert np.array_equal(out, data)
+
+
+def test_golden_acs_small(golden_dir):
+    g = _golden(golden_dir, "acs_small.npz")
+    for nm in g["names"]:
+        prec, cdf, toks = int(g[f"{nm}/prec"]), g[f"{nm}/cdf"], g[f"{nm}/toks"].astype(np.int32)
+        T = len(toks)
+        enc = coder.StreamEncoder(1, prec=prec, capacity_bytes=T * 8 + 64)
+        enc.acs_encode_tables(_dev(cdf.view(np.int64)), _dev(toks[None]), finish=True)
+        streams, nbits = enc.bitstreams()
+        assert nbits[0] == len(g[f"{nm}/bits"]), nm
+        assert streams[0] == orc.pack_bits(g[f"{nm}/bits"]).tobytes(), nm
+        # our decoder always round-trips (the reference's own expand path does not: DESIGN.md section 6)
+        out = coder.StreamDecoder(streams, prec=prec).acs_decode_tables(_dev(cdf.view(np.int64)), T)
+        assert np.array_equal(out.cpu().numpy()[0], toks), nm
+
+
+def test_golden_acs_64k_config0(golden_dir):
+    """BASELINE config[0]: 64 KB synthetic bytes, adaptive frequency model, ACSampler coder."""
+    g = _golden(golden_dir, "acs_64k.npz")
+    data = g["data"]
+    T, prec = len(data), int(g["prec"])
+    tabs = _dev(_adaptive_tables(data))
+    enc = coder.StreamEncoder(1, prec=prec, capacity_bytes=T)
+    enc.acs_encode_tables(tabs, _dev(data.astype(np.int32)[None]), finish=True)
+    streams, _ = enc.bitstreams()
+    assert streams[0] == g["comp"].tobytes()
+    out = coder.StreamDecoder(streams, prec=prec).acs_decode_tables(tabs, T).cpu().numpy()[0]
+    assert np.array_equal(out, data)
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_size_slice_roundtrip_and_size():
+    """BASELINE config[1] shape (vocab 32000, 1024 streams), a 4-token slice: lossless round trip and the
+    coded size within a few bits per stream of the ideal code length of the LQ32 tables."""
+    S, T, V = 1024, 4, 32000
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    logits = torch.randn((S, T, V), generator=gen, device="cuda") * 3.0
+    syms = torch.multinomial(torch.softmax(logits.view(S * T, V), dim=-1), 1, generator=gen).view(S, T).to(torch.int32)
+    enc = coder.StreamEncoder(S, capacity_bytes=T * 8 + 64)
+    enc.encode_logits(logits, syms, finish=True)
+    streams, nbits = enc.bitstreams()
+    back = coder.StreamDecoder(streams).decode_logits(logits)
+    assert torch.equal(back, syms)
+    pairs = coder.u32(coder.cdf_lookup(logits.view(S * T, V), syms.view(-1)))
+    hi = torch.where(pairs[:, 1] == 0, torch.full_like(pairs[:, 1], 1 << 32), pairs[:, 1])
+    ideal = (32.0 - torch.log2((hi - pairs[:, 0]).double())).view(S, T).sum(1).cpu().numpy()
+    assert (nbits.astype(np.float64) <= ideal + 3).all() and (nbits.astype(np.float64) >= ideal - 1).all()
+    # spot-check 3 streams bit-exact against the oracle at full vocab
+    lg, sy = logits.cpu().numpy(), syms.cpu().numpy()
+    for s in (0, 511, 1023):
+        assert streams[s] == _oracle_stream(lg[s], sy[s], 48)
+
+
+def test_host_buffer_api_roundtrip():
+    rng = np.random.default_rng(9)
+    S, T, V = 12, 10, 32000
+    logits = (rng.standard_normal((S, T, V)) * 2).astype(np.float32)
+    syms = rng.integers(0, V, (S, T)).astype(np.int32)
+    out, nbits = coder.encode_logits_host(logits, syms)
+    nbytes = (nbits + 7) // 8
+    offs = np.zeros(S + 1, dtype=np.int64)
+    offs[1:] = np.cumsum(nbytes)
+    data = np.concatenate([out[s, :nbytes[s]] for s in range(S)] + [np.zeros(16, np.uint8)])
+    for s in (0, S - 1):
+        assert out[s, :nbytes[s]].tobytes() == _oracle_stream(logits[s], syms[s], 48)
+    back = coder.decode_logits_host(logits, data, offs)
+    assert np.array_equal(back, syms)
