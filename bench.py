@@ -121,9 +121,11 @@ def cpu_baseline_leg(target_seconds=12.0):
     lg, sy = cpu_sample(cores, 2, seed=2)
     t0 = time.perf_counter()
     orc.ref_roundtrip_bulk(lg, sy, prec=PREC)
-    per_tok = (time.perf_counter() - t0) / 2  # one stream per core, 2 tokens each
-    T = int(max(2, min(64, target_seconds / max(per_tok, 1e-6) / 4)))
-    streams = cores * 4
+    per_tok = (time.perf_counter() - t0) / 2  # seconds per token on one core (one stream per core, 2 tokens each)
+    total = int(target_seconds * cores / max(per_tok, 1e-6))  # tokens worth ~target_seconds of wall time
+    total = max(cores * 4, min(total, 12288))                 # <= 1.6 GB of host logits
+    T = 16
+    streams = max(cores, total // T)
     lg, sy = cpu_sample(streams, T, seed=3)
     t0 = time.perf_counter()
     bad, bits = orc.ref_roundtrip_bulk(lg, sy, prec=PREC)

@@ -146,10 +146,13 @@ int lac_ac_decode_tables(const int64_t *d_dist, int32_t vocab, int64_t stream_st
                          int64_t sym_stride, int prec, int flags, void *stream);
 
 /* ACSampler semantics (arithmetic_coding.py): uint64 inclusive cumulative tables as
- * sample_scaled_cdf receives them, denominator = table[-1]; finish runs flush_compress()
- * and packbits.flush().  The decoder returns the symbol whose encoder interval contains the
- * code value (the reference's own expand path mis-decodes interval boundaries and stream
- * tails). */
+ * sample_scaled_cdf receives them, denominator = table[-1].
+ * finish = 1: flush_compress() + packbits.flush(), bit-exact with the reference.  That flush
+ *   does not pin the final interval, so the last tokens of such a stream can be undecodable
+ *   by any decoder (the reference's own expand path round-trips 16 of the 30 golden cases).
+ * finish = 2: safe termination (A_to_bin.flush on the Region state): always decodable.
+ * The decoder returns the symbol whose encoder interval contains the zero-padded code value
+ * (DESIGN.md section 6). */
 int lac_acs_encode_tables(const uint64_t *d_cdf, int32_t vocab, int64_t stream_stride, int64_t tok_stride,
                           const int32_t *d_syms, int64_t n_streams, int64_t T, const int32_t *d_ntok,
                           lac_enc_state *d_state, uint8_t *d_out, int64_t out_stride, int finish,

@@ -143,16 +143,18 @@ class StreamEncoder:
         self.finished = self.finished or finish
 
     def acs_encode_tables(self, cdf: torch.Tensor, syms: torch.Tensor, ntok: Optional[torch.Tensor] = None,
-                          finish: bool = False):
-        """ACSampler semantics (arithmetic_coding.py:73-93): int64-carried uint64 inclusive tables."""
+                          finish=False):
+        """ACSampler semantics (arithmetic_coding.py:73-93): int64-carried uint64 inclusive tables.
+        finish=True: the reference's flush_compress (bit-exact; tail tokens may be undecodable);
+        finish="safe": A_to_bin-style termination, always decodable."""
         _need_cuda(cdf, "cdf", torch.int64)
         _need_cuda(syms, "syms", torch.int32)
         S, T = syms.shape
         V, ss, ts, _, _ = _table_strides(cdf, None, S, T)
         check(lib().lac_acs_encode_tables(cdf.data_ptr(), V, ss, ts, syms.data_ptr(), S, T, self._ntok(ntok),
-                                          self.state.data_ptr(), self.out.data_ptr(), self.cap, int(finish),
-                                          self.prec, _cur_stream()))
-        self.finished = self.finished or finish
+                                          self.state.data_ptr(), self.out.data_ptr(), self.cap,
+                                          2 if finish == "safe" else int(bool(finish)), self.prec, _cur_stream()))
+        self.finished = self.finished or bool(finish)
 
     def finish(self):
         if not self.finished:

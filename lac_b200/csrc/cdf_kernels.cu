@@ -1,18 +1,27 @@
 // cdf_kernels.cu -- fused logits -> LQ32 CDF kernels (north-star part (a)) and the fused
 // decode step (part (b), decoder side).
 //
-// One CTA of 1024 threads owns one logits row at a time and keeps it in registers: warp w
-// owns a contiguous segment of the row, lanes stride through it with 128-bit loads.  The
-// row is read from HBM exactly once:
-//   phase A  row max                      (warp shuffle + one block barrier)
-//   phase B  q_i, exact integer sums      (per lane -> per warp -> 32 warp totals in smem)
-//   final    LOOKUP: cum[sym], cum[sym+1] from masked integer sums (no table written)
-//            BUILD : whole table via in-warp exclusive scans
-//            DECODE: hierarchical search warp -> 128-wide slab -> lane -> element for the
-//                    symbol whose coder interval contains the code value, then the
-//                    A_from_bin state update, all inside the kernel.
+// One persistent CTA of 1024 threads per SM walks its rows.  Warp w owns a contiguous
+// segment of the row; the row is read from HBM exactly once and then lives in registers:
+//
+//   staging  the row arrives as NCH TMA bulk copies (cp.async.bulk; 2 x 64 KB by default) into a
+//            shared-memory ring, each chunk with its own mbarrier.  As soon as the warps of a chunk
+//            have moved it to registers they re-arm the barrier and issue the bulk copy of the SAME
+//            chunk of the CTA's NEXT row, so 128 KB per SM stay in flight during the compute phases.
+//   phase A  row max                      (REDUX + the one block barrier of the row)
+//   phase B  q_i with packed fp32x2 math (FADD2 / FFMA2), exact integer sums (lane -> warp)
+//   finish   the LAST warp to finish phase B (shared-memory atomic counter) does the row-level
+//            bookkeeping once -- prefix of the 32 warp totals, the scale (one division), for decode
+//            the owner warp -- and arrives on the `done` mbarrier; there is no second block barrier.
+//   final    LOOKUP: only the warp that owns the coded symbol waits for `done`; it writes
+//                    cum[sym], cum[sym+1] from masked integer sums (no table is written); the other
+//                    31 warps are already draining the next row.
+//            BUILD : whole table via in-warp exclusive scans.
+//            DECODE: 8 interleaved lane scans + ballots locate the 4-element group in the owner warp,
+//                    one lane finishes the search and runs the A_from_bin state update.
 // The integer formulation (lq32.cuh) makes the result independent of this decomposition.
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "coder.cuh"
@@ -23,6 +32,58 @@ namespace lac {
 constexpr int kThreads = 1024;
 constexpr int kWarps = kThreads / 32;
 constexpr int kPerThread = 32;  // row elements held per thread
+
+// TMA chunks per row.  Measured on B200 (profiles/microbench/tma_stream.cu): every cp.async.bulk costs
+// ~0.2 us of per-SM TMA time regardless of size, so 8 x 16 KB chunks cap at 4.7 TB/s while 2 x 64 KB
+// reach 7.2 TB/s with the same 128 KB in flight.
+constexpr int kMaxChunks = 8;
+template <int NCH>
+struct Ring {
+    static constexpr int kWarpsPerChunk = kWarps / NCH;
+    static constexpr int kSlotGroups = kPerThread / 4 * 32 * kWarpsPerChunk + 1;  // float4 groups per slot
+    static constexpr int kSlotBytes = kSlotGroups * 16;
+    static constexpr int kRingBytes = NCH * kSlotBytes;
+};
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar` (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_acq_rel_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
     float4 v;
@@ -37,17 +98,59 @@ __device__ __forceinline__ float ldg_stream1(const float* p) {
     return v;
 }
 
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = lq::vmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
+// ------------------------------------------------------------------ packed fp32x2 (FADD2 / FFMA2)
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
 }
-__device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
 }
-// inclusive prefix over lanes
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// Two q values at once: exactly lq::q_of's operations (explicit FMAs -- ptxas contracts packed
+// mul+add pairs on its own, so the spec fuses them by definition), two lanes per instruction:
+// FADD2, FFMA2, FADD2, FFMA2, 3 x FFMA2 per pair, then shl / funnel-shift per element.  No F2I.
+__device__ __forceinline__ void q_of2(float xa, float xb, uint64_t m2, uint32_t& qa, uint32_t& qb) {
+    const uint64_t L2 = pk2(lq::log2e(), lq::log2e());
+    const uint64_t MG = pk2(lq::magic(), lq::magic());
+    uint64_t d = sub2(pk2(xa, xb), m2);
+    uint64_t t = fma2(d, L2, MG);
+    uint64_t rn = sub2(MG, t);
+    uint64_t f = fma2(d, L2, rn);
+    uint64_t p = pk2(__uint_as_float(lq::kC3), __uint_as_float(lq::kC3));
+    p = fma2(p, f, pk2(__uint_as_float(lq::kC2), __uint_as_float(lq::kC2)));
+    p = fma2(p, f, pk2(__uint_as_float(lq::kC1), __uint_as_float(lq::kC1)));
+    uint64_t z = fma2(p, f, MG);
+    float za, zb, ta, tb;
+    upk2(z, za, zb);
+    upk2(t, ta, tb);
+    qa = __funnelshift_rc(__float_as_uint(za) << 9, 0u, 0x4B400000u - __float_as_uint(ta));
+    qb = __funnelshift_rc(__float_as_uint(zb) << 9, 0u, 0x4B400000u - __float_as_uint(tb));
+}
+
+// ------------------------------------------------------------------ warp collectives (REDUX where possible)
+__device__ __forceinline__ int f2ord(float f) {  // order-preserving float -> int (no NaNs reach here)
+    int b = __float_as_int(f);
+    return b ^ ((b >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float ord2f(int o) { return __int_as_float(o ^ ((o >> 31) & 0x7fffffff)); }
+__device__ __forceinline__ float warp_max(float v) { return ord2f(__reduce_max_sync(0xffffffffu, f2ord(v))); }
+// sum over the warp of values < 2^48: three 16-bit limbs through REDUX.SUM
+__device__ __forceinline__ uint64_t warp_sum48(uint64_t v) {
+    uint32_t a = __reduce_add_sync(0xffffffffu, (uint32_t)v & 0xffffu);
+    uint32_t b = __reduce_add_sync(0xffffffffu, (uint32_t)(v >> 16) & 0xffffu);
+    uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)(v >> 32));
+    return (uint64_t)a + ((uint64_t)b << 16) + ((uint64_t)c << 32);
+}
 __device__ __forceinline__ uint64_t warp_incl_scan(uint64_t v, int lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -57,142 +160,301 @@ __device__ __forceinline__ uint64_t warp_incl_scan(uint64_t v, int lane) {
     return v;
 }
 
+// ------------------------------------------------------------------ shared control block
 struct DecShared {
     int64_t low, high, value;
-    uint64_t pos;
+    uint64_t pos;             // next bit of the stream
+    uint64_t win_hi, win_lo;  // 16 stream bytes starting at byte win_byte, big-endian
+    uint64_t win_byte;
+    int64_t data_off;
+    uint64_t nbytes;
     uint32_t status;
 };
 
-struct Smem {
-    float red_max[kWarps];
-    uint64_t wsum[kWarps];
-    DecShared dec;
+struct Ctl {
+    uint64_t full[kMaxChunks];  // TMA chunk landed
+    uint64_t done;              // row-level bookkeeping published (phase = row parity)
+    float red_max[2][kWarps];   // per-warp maxima, double-buffered by row parity
+    uint64_t wsum[kWarps];      // per-warp totals of q
+    uint64_t pref[kWarps];      // exclusive prefix of wsum   } written once per row by the last warp
+    uint64_t Q;                 // sum of wsum                } to finish phase B, then `done` flips
+    uint32_t R;                 // lq::Scale                  }
+    int s;                      //                            }
+    int owner;                  // decode: warp whose segment holds the symbol
+    uint32_t arrive;            // warps done with phase B of the current row
+    DecShared dec[2];
 };
 
-// Phases A and B for one row.  On return q[] holds this thread's q values (0 for slots
-// outside the row), sm.wsum[] the 32 warp totals (valid after the trailing barrier).
-template <int VEC>
-__device__ __forceinline__ void row_reduce(const float* __restrict__ row, int G, int warp, int lane,
-                                           Smem& sm, uint32_t (&q)[kPerThread], int& gbeg, int& gend) {
-    constexpr int IT = kPerThread / VEC;
-    gbeg = (int)(((int64_t)warp * G) / kWarps);
-    gend = (int)(((int64_t)(warp + 1) * G) / kWarps);
-    float x[kPerThread];
-#pragma unroll
-    for (int k = 0; k < IT; k++) {
-        int g = gbeg + k * 32 + lane;
-        if (VEC == 4) {
-            float4 v = make_float4(lq::neg_inf(), lq::neg_inf(), lq::neg_inf(), lq::neg_inf());
-            if (g < gend) v = ldg_stream4(row + 4 * (int64_t)g);
-            x[4 * k + 0] = v.x;
-            x[4 * k + 1] = v.y;
-            x[4 * k + 2] = v.z;
-            x[4 * k + 3] = v.w;
-        } else {
-            x[k] = g < gend ? ldg_stream1(row + g) : lq::neg_inf();
+// Rows visited by this CTA, in order: outer index s = blockIdx.x, += gridDim.x; inner t < Ts.
+// RowParams stays in the kernel-parameter constant bank; only (s, t, Ts) live in registers.
+struct RowParams {
+    const float* base;
+    int64_t n_outer, T, so, st;
+    const int32_t* ntok;
+};
+struct RowSeq {
+    int64_t s;
+    int t, Ts;
+    __device__ __forceinline__ void skip_empty(const RowParams& p) {
+        while (s < p.n_outer) {
+            Ts = p.ntok ? p.ntok[s] : (int)p.T;
+            if (Ts > 0) break;
+            s += gridDim.x;
         }
     }
-    float m = lq::neg_inf();
-#pragma unroll
-    for (int i = 0; i < kPerThread; i++) m = lq::vmax(m, x[i]);
-    m = warp_max(m);
-    if (lane == 0) sm.red_max[warp] = m;
-    __syncthreads();
-    m = warp_max(sm.red_max[lane]);
-    uint64_t lane_sum = 0;
-#pragma unroll
-    for (int i = 0; i < kPerThread; i++) {
-        q[i] = lq::q_of(x[i], m);
-        lane_sum += q[i];
+    __device__ __forceinline__ void init(const RowParams& p) {
+        s = blockIdx.x;
+        t = 0;
+        Ts = 0;
+        skip_empty(p);
     }
-    uint64_t ws = warp_sum(lane_sum);
-    if (lane == 0) sm.wsum[warp] = ws;
-    __syncthreads();
-}
+    __device__ __forceinline__ bool valid(const RowParams& p) const { return s < p.n_outer; }
+    __device__ __forceinline__ const float* ptr(const RowParams& p) const { return p.base + s * p.so + t * p.st; }
+    __device__ __forceinline__ void next(const RowParams& p) {
+        if (++t >= Ts) {
+            s += gridDim.x;
+            t = 0;
+            skip_empty(p);
+        }
+    }
+};
 
-// Prefix of the warp totals: C at the start of `warp`'s segment, and Q.
-__device__ __forceinline__ void warp_prefix(const Smem& sm, int warp, int lane, uint64_t& Cb, uint64_t& Q) {
-    uint64_t v = sm.wsum[lane];
-    uint64_t inc = warp_incl_scan(v, lane);
-    Q = __shfl_sync(0xffffffffu, inc, 31);
-    uint64_t exc = inc - v;
-    Cb = __shfl_sync(0xffffffffu, exc, warp);
-}
+// ------------------------------------------------------------------ row engine: staging + phases A, B + finish
+template <int VEC, bool TMA, int NCH>
+struct RowEngine {
+    static constexpr int IT = kPerThread / VEC;
+    static constexpr int kWarpsPerChunk = Ring<NCH>::kWarpsPerChunk;
+    static constexpr int kSlotBytes = Ring<NCH>::kSlotBytes;
+    int warp, lane, V, G, gbeg, gend;
+    int cg0;
+    uint32_t cbytes, it;
+    Ctl* ctl;
+    unsigned char* ring;
+    __device__ __forceinline__ int chunk() const { return warp / kWarpsPerChunk; }
+    __device__ __forceinline__ bool leader() const { return (warp % kWarpsPerChunk == 0) && lane == 0; }
+    __device__ __forceinline__ unsigned char* slot() const { return ring + chunk() * kSlotBytes; }
 
-__device__ __forceinline__ lq::Scale bcast_scale(uint64_t Q, int V, int lane) {
-    lq::Scale k;
-    k.Q = Q;
-    k.R = 0;
-    k.s = 0;
-    if (lane == 0) k = lq::make_scale(Q, V);
-    k.R = __shfl_sync(0xffffffffu, k.R, 0);
-    k.s = __shfl_sync(0xffffffffu, k.s, 0);
-    return k;
-}
+    __device__ void setup(int V_, Ctl* c, unsigned char* ring_) {
+        warp = threadIdx.x >> 5;
+        lane = threadIdx.x & 31;
+        V = V_;
+        G = V / VEC;
+        gbeg = (int)(((int64_t)warp * G) / kWarps);
+        gend = (int)(((int64_t)(warp + 1) * G) / kWarps);
+        ctl = c;
+        ring = ring_;
+        it = 0;
+        cg0 = 0;
+        cbytes = 0;
+        if (TMA) {
+            cg0 = (int)(((int64_t)(chunk() * kWarpsPerChunk) * G) / kWarps);
+            int cg1 = (int)(((int64_t)((chunk() + 1) * kWarpsPerChunk) * G) / kWarps);
+            cbytes = (uint32_t)(cg1 - cg0) * 16u;
+        }
+        if (threadIdx.x == 0) {
+            c->arrive = 0;
+            for (int i = 0; i < NCH; i++) mbar_init(&ctl->full[i], 1);
+            mbar_init(&ctl->done, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+    }
+    __device__ __forceinline__ void issue(const float* row) {  // chunk leader: arm + bulk copy of this chunk
+        if (TMA && leader() && cbytes) {
+            mbar_expect_tx(&ctl->full[chunk()], cbytes);
+            tma_load_1d(slot(), row + 4 * (int64_t)cg0, cbytes, &ctl->full[chunk()], evict_first_policy());
+        }
+    }
+
+    // Phases A and B for `row`; `next_row` (or nullptr) is prefetched as soon as this row has left shared
+    // memory.  On return q[] holds this thread's q values; the row-level results (ctl->pref, Q, R, s,
+    // owner) are valid once wait_done() returns.
+    __device__ __forceinline__ void reduce(const float* __restrict__ row, const float* next_row,
+                                           uint32_t (&q)[kPerThread], const DecShared* dec = nullptr) {
+        float x[kPerThread];
+        if (TMA) {
+            if (cbytes) mbar_wait(&ctl->full[chunk()], it & 1);
+            const unsigned char* sl = slot();
+#pragma unroll
+            for (int k = 0; k < IT; k++) {
+                int g = gbeg + k * 32 + lane;
+                float4 v = make_float4(lq::neg_inf(), lq::neg_inf(), lq::neg_inf(), lq::neg_inf());
+                if (g < gend) v = *reinterpret_cast<const float4*>(sl + (size_t)(g - cg0) * 16);
+                x[4 * k + 0] = v.x;
+                x[4 * k + 1] = v.y;
+                x[4 * k + 2] = v.z;
+                x[4 * k + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < IT; k++) {
+                int g = gbeg + k * 32 + lane;
+                if (VEC == 4) {
+                    float4 v = make_float4(lq::neg_inf(), lq::neg_inf(), lq::neg_inf(), lq::neg_inf());
+                    if (g < gend) v = ldg_stream4(row + 4 * (int64_t)g);
+                    x[4 * k + 0] = v.x;
+                    x[4 * k + 1] = v.y;
+                    x[4 * k + 2] = v.z;
+                    x[4 * k + 3] = v.w;
+                } else {
+                    x[k] = g < gend ? ldg_stream1(row + g) : lq::neg_inf();
+                }
+            }
+        }
+        float m = lq::neg_inf();
+#pragma unroll
+        for (int i = 0; i < kPerThread; i++) m = lq::vmax(m, x[i]);
+        if (TMA) {
+            // every thread's max depends on all its shared-memory loads, so after this barrier the
+            // chunk is fully in registers and the slot can be overwritten by the next row
+            named_bar_sync(1 + chunk(), 32 * kWarpsPerChunk);
+            if (next_row) {
+                if (leader()) fence_proxy_async();
+                issue(next_row);
+            }
+        }
+        m = warp_max(m);
+        float* red = ctl->red_max[it & 1];
+        if (lane == 0) red[warp] = m;
+        __syncthreads();  // the only block-wide barrier of the row
+        m = warp_max(red[lane]);
+        const uint64_t m2 = pk2(m, m);
+        uint64_t lane_sum = 0;
+#pragma unroll
+        for (int i = 0; i < kPerThread; i += 2) {
+            q_of2(x[i], x[i + 1], m2, q[i], q[i + 1]);
+            lane_sum += q[i];
+            lane_sum += q[i + 1];
+        }
+        const uint64_t ws = warp_sum48(lane_sum);
+        uint32_t prev = 0;
+        if (lane == 0) {
+            ctl->wsum[warp] = ws;
+            fence_acq_rel_cta();
+            prev = atomicAdd(&ctl->arrive, 1u);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, 0);
+        if (prev == kWarps - 1) {  // last warp of the row: every wsum[] is visible
+            fence_acq_rel_cta();
+            const uint64_t v = *reinterpret_cast<volatile uint64_t*>(&ctl->wsum[lane]);
+            const uint64_t inc = warp_incl_scan(v, lane);
+            const uint64_t Q = __shfl_sync(0xffffffffu, inc, 31);
+            const uint64_t exc = inc - v;
+            ctl->pref[lane] = exc;
+            lq::Scale sc;
+            sc.Q = Q;
+            sc.R = 0;
+            sc.s = 0;
+            if (lane == 0) sc = lq::make_scale(Q, V);
+            sc.R = __shfl_sync(0xffffffffu, sc.R, 0);
+            sc.s = __shfl_sync(0xffffffffu, sc.s, 0);
+            if (dec) {  // lane w tests warp w's segment start: the owner is the last non-empty one at or below the value
+                const int gb = (int)(((int64_t)lane * G) / kWarps), ge = (int)(((int64_t)(lane + 1) * G) / kWarps);
+                const uint64_t w = (uint64_t)(dec->high - dec->low + 1), xr = (uint64_t)(dec->value - dec->low);
+                const bool ok = gb < ge && coder::scale32_ceil(lq::cum_of(exc, (uint32_t)(gb * VEC), sc), w) <= xr;
+                const unsigned ball = __ballot_sync(0xffffffffu, ok);
+                if (lane == 0) ctl->owner = 31 - __clz((int)ball);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                ctl->Q = Q;
+                ctl->R = sc.R;
+                ctl->s = sc.s;
+                ctl->arrive = 0;
+                mbar_arrive(&ctl->done);  // release: publishes everything above
+            }
+        }
+        it++;
+    }
+    // Block until the row-level results of the row just reduce()d are published.
+    __device__ __forceinline__ void wait_done() const { mbar_wait(&ctl->done, (it - 1) & 1); }
+    __device__ __forceinline__ lq::Scale scale() const {
+        lq::Scale sc;
+        sc.Q = ctl->Q;
+        sc.R = ctl->R;
+        sc.s = ctl->s;
+        return sc;
+    }
+};
+
+extern __shared__ __align__(128) unsigned char g_ring[];
 
 // ------------------------------------------------------------------ LOOKUP
-template <int VEC>
+template <int VEC, bool TMA, int NCH>
 __global__ void __launch_bounds__(kThreads, 1)
-lookup_kernel(const float* __restrict__ logits, int64_t rows, int V, int64_t row_stride,
-              const int32_t* __restrict__ syms, uint32_t* __restrict__ pairs, uint32_t* __restrict__ status) {
-    __shared__ Smem sm;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int G = V / VEC;
-    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+lookup_kernel(const __grid_constant__ RowParams rp, int V, const int32_t* __restrict__ syms,
+              uint32_t* __restrict__ pairs, uint32_t* __restrict__ status) {
+    __shared__ Ctl ctl;
+    RowEngine<VEC, TMA, NCH> eng;
+    eng.setup(V, &ctl, g_ring);
+    const int warp = eng.warp, lane = eng.lane, gbeg = eng.gbeg, gend = eng.gend;
+    RowSeq seq;
+    seq.init(rp);
+    if (seq.valid(rp)) eng.issue(seq.ptr(rp));
+    while (seq.valid(rp)) {
+        const int64_t r = seq.s;
+        const float* row = seq.ptr(rp);
+        const int sym = __ldg(syms + r);  // issued now, consumed after the row's compute phases
+        seq.next(rp);
         uint32_t q[kPerThread];
-        int gbeg, gend;
-        row_reduce<VEC>(logits + r * row_stride, G, warp, lane, sm, q, gbeg, gend);
-        const int sym = syms[r];
+        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, q);
         if (sym < 0 || sym >= V) {
             if (threadIdx.x == 0) {
-                pairs[2 * r] = 0;
-                pairs[2 * r + 1] = 0;
+                *reinterpret_cast<uint2*>(pairs + 2 * r) = make_uint2(0u, 0u);
                 if (status) atomicOr(status + r, LAC_ST_SYMBOL);
             }
             continue;
         }
         const int gs = sym / VEC, es = sym % VEC;
-        if (gs < gbeg || gs >= gend) continue;  // not the owner warp
-        uint64_t Cb, Q;
-        warp_prefix(sm, warp, lane, Cb, Q);
-        uint64_t part = 0, qs = 0;
-        constexpr int IT = kPerThread / VEC;
+        if (gs >= gbeg && gs < gend) {  // owner warp; everyone else is already on the next row
+            uint64_t part = 0, qs = 0;
+            constexpr int IT = kPerThread / VEC;
 #pragma unroll
-        for (int k = 0; k < IT; k++) {
-            int g = gbeg + k * 32 + lane;
+            for (int k = 0; k < IT; k++) {
+                int g = gbeg + k * 32 + lane;
 #pragma unroll
-            for (int e = 0; e < VEC; e++) {
-                uint32_t v = q[k * VEC + e];
-                if (g < gs || (g == gs && e < es)) part += v;
-                if (g == gs && e == es) qs = v;
+                for (int e = 0; e < VEC; e++) {
+                    uint32_t v = q[k * VEC + e];
+                    if (g < gs || (g == gs && e < es)) part += v;
+                    if (g == gs && e == es) qs = v;
+                }
             }
-        }
-        part = warp_sum(part);
-        qs = warp_sum(qs);
-        if (lane == 0) {
-            lq::Scale sc = lq::make_scale(Q, V);
-            uint64_t C = Cb + part;
-            pairs[2 * r] = lq::cum_of(C, (uint32_t)sym, sc);
-            pairs[2 * r + 1] = (sym == V - 1) ? 0u : lq::cum_of(C + qs, (uint32_t)sym + 1, sc);
+            part = warp_sum48(part);
+            qs = warp_sum48(qs);
+            eng.wait_done();
+            if (lane == 0) {
+                const lq::Scale sc = eng.scale();
+                const uint64_t C = ctl.pref[warp] + part;
+                uint2 o;
+                o.x = lq::cum_of(C, (uint32_t)sym, sc);
+                o.y = (sym == V - 1) ? 0u : lq::cum_of(C + qs, (uint32_t)sym + 1, sc);
+                *reinterpret_cast<uint2*>(pairs + 2 * r) = o;
+            }
+            __syncwarp();
         }
     }
 }
 
 // ------------------------------------------------------------------ BUILD
-template <int VEC>
+template <int VEC, bool TMA, int NCH>
 __global__ void __launch_bounds__(kThreads, 1)
-build_kernel(const float* __restrict__ logits, int64_t rows, int V, int64_t row_stride,
-             uint32_t* __restrict__ cum) {
-    __shared__ Smem sm;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int G = V / VEC;
-    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+build_kernel(const __grid_constant__ RowParams rp, int V, uint32_t* __restrict__ cum) {
+    __shared__ Ctl ctl;
+    RowEngine<VEC, TMA, NCH> eng;
+    eng.setup(V, &ctl, g_ring);
+    const int warp = eng.warp, lane = eng.lane, gbeg = eng.gbeg, gend = eng.gend;
+    RowSeq seq;
+    seq.init(rp);
+    if (seq.valid(rp)) eng.issue(seq.ptr(rp));
+    while (seq.valid(rp)) {
+        const int64_t r = seq.s;
+        const float* row = seq.ptr(rp);
+        seq.next(rp);
         uint32_t q[kPerThread];
-        int gbeg, gend;
-        row_reduce<VEC>(logits + r * row_stride, G, warp, lane, sm, q, gbeg, gend);
-        uint64_t base, Q;
-        warp_prefix(sm, warp, lane, base, Q);
-        lq::Scale sc = bcast_scale(Q, V, lane);
+        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, q);
+        eng.wait_done();
+        uint64_t base = ctl.pref[warp];
+        const lq::Scale sc = eng.scale();
         uint32_t* out = cum + r * (int64_t)V;
         constexpr int IT = kPerThread / VEC;
 #pragma unroll
@@ -224,121 +486,161 @@ build_kernel(const float* __restrict__ logits, int64_t rows, int V, int64_t row_
 }
 
 // ------------------------------------------------------------------ DECODE
-// lowest coder offset of a symbol whose exclusive cumulative is c: ceil(c * w / 2^32)
-// (symbol_to_range's l, arith_code.py:110-111); val_to_symbol (arith_code.py:94-101) picks
-// the last symbol with lowpos <= value - l.
-__device__ __forceinline__ uint64_t lowpos(uint32_t c, uint64_t w) { return coder::scale32_ceil(c, w); }
+// val_to_symbol (arith_code.py:94-101) on the total d = 2^32 picks the last symbol whose lowest
+// coder offset ceil(cum * w / 2^32) (symbol_to_range's l, arith_code.py:110-111) is <= x = value - l.
+// Comparing through the multiplication keeps 128-bit divisions off the per-token serial path.
+__device__ __forceinline__ bool cum_le(uint32_t cum, uint64_t x, uint64_t w) { return coder::scale32_ceil(cum, w) <= x; }
 
-template <int VEC>
+// 8 stream bytes at byte offset b as a big-endian word, zeros past the end
+__device__ __forceinline__ uint64_t load_be64(const uint8_t* data, uint64_t nbytes, uint64_t b) {
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) v = (v << 8) | (uint64_t)((b + i) < nbytes ? data[b + i] : 0);
+    return v;
+}
+
+__device__ __forceinline__ void dec_load_state(DecShared& d, const lac_dec_state* st, const uint8_t* bytes,
+                                               const int64_t* offsets, int64_t s) {
+    d.low = st[s].low;
+    d.high = st[s].high;
+    d.value = st[s].value;
+    d.pos = st[s].pos;
+    d.status = st[s].status;
+    d.data_off = offsets[s];
+    d.nbytes = (uint64_t)(offsets[s + 1] - offsets[s]);
+    d.win_byte = d.pos >> 3;
+    d.win_hi = load_be64(bytes + d.data_off, d.nbytes, d.win_byte);
+    d.win_lo = load_be64(bytes + d.data_off, d.nbytes, d.win_byte + 8);
+}
+
+template <int VEC, bool TMA, int NCH>
 __global__ void __launch_bounds__(kThreads, 1)
-decode_kernel(const float* __restrict__ logits, int64_t n_streams, int64_t T, int64_t stream_stride,
-              int64_t tok_stride, int V, const int32_t* __restrict__ ntok, lac_dec_state* __restrict__ state,
+decode_kernel(const __grid_constant__ RowParams rp, int V, lac_dec_state* __restrict__ state,
               const uint8_t* __restrict__ bytes, const int64_t* __restrict__ offsets,
               int32_t* __restrict__ syms, int64_t sym_stride, int P) {
-    __shared__ Smem sm;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int G = V / VEC;
+    __shared__ Ctl ctl;
+    RowEngine<VEC, TMA, NCH> eng;
+    eng.setup(V, &ctl, g_ring);
+    const int warp = eng.warp, lane = eng.lane, gbeg = eng.gbeg, gend = eng.gend;
     constexpr int IT = kPerThread / VEC;
-    for (int64_t s = blockIdx.x; s < n_streams; s += gridDim.x) {
-        __syncthreads();  // previous stream's state fully written back
-        if (threadIdx.x == 0) {
-            sm.dec.low = state[s].low;
-            sm.dec.high = state[s].high;
-            sm.dec.value = state[s].value;
-            sm.dec.pos = state[s].pos;
-            sm.dec.status = state[s].status;
+    RowSeq seq;
+    seq.init(rp);
+    if (seq.valid(rp)) eng.issue(seq.ptr(rp));
+    uint32_t par = 0;  // which DecShared buffer the current stream uses
+    while (seq.valid(rp)) {
+        const int64_t s = seq.s;
+        const int t = seq.t;
+        const bool first = (t == 0), last = (t == seq.Ts - 1);
+        const float* row = seq.ptr(rp);
+        seq.next(rp);
+        if (first) {
+            // double-buffered by stream parity: the previous stream's owner lane may still be
+            // finishing with the other buffer; published by the block barrier inside reduce()
+            par ^= 1;
+            if (threadIdx.x == 0) dec_load_state(ctl.dec[par], state, bytes, offsets, s);
         }
-        const uint8_t* data = bytes + offsets[s];
-        const uint64_t nbytes = (uint64_t)(offsets[s + 1] - offsets[s]);
-        const int64_t Ts = ntok ? (int64_t)ntok[s] : T;
-        for (int64_t t = 0; t < Ts; t++) {
-            uint32_t q[kPerThread];
-            int gbeg, gend;
-            // the two barriers inside also publish sm.dec written by the previous owner lane
-            row_reduce<VEC>(logits + s * stream_stride + t * tok_stride, G, warp, lane, sm, q, gbeg, gend);
-            const int64_t l = sm.dec.low, h = sm.dec.high;
-            const uint64_t w = (uint64_t)(h - l + 1);
-            const uint64_t xr = (uint64_t)(sm.dec.value - l);
-            uint64_t Cb, Q;
-            warp_prefix(sm, warp, lane, Cb, Q);
-            lq::Scale sc = bcast_scale(Q, V, lane);
-            const uint64_t Cn = Cb + sm.wsum[warp];
-            const uint64_t low_b = lowpos(lq::cum_of(Cb, (uint32_t)(gbeg * VEC), sc), w);
-            const uint64_t low_n = (gend == G) ? w : lowpos(lq::cum_of(Cn, (uint32_t)(gend * VEC), sc), w);
-            if (!(gbeg < gend && low_b <= xr && xr < low_n)) continue;  // not the owner warp
-            // ---- slab (k) level
-            uint64_t Ck = Cb, Csel = Cb;
-            int ksel = 0;
+        uint32_t q[kPerThread];
+        DecShared& dec = ctl.dec[par];
+        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, q, &dec);
+        eng.wait_done();
+        if (warp == ctl.owner) {
+            const uint64_t w = (uint64_t)(dec.high - dec.low + 1);
+            const uint64_t xr = (uint64_t)(dec.value - dec.low);
+            const lq::Scale sc = eng.scale();
+            const uint64_t Cb = ctl.pref[warp];
+            // ---- owner warp: IT interleaved lane scans of the group sums, then one ballot per slab.
+            // Groups are ordered (slab k, lane); cum is monotone in that order, so the number of groups
+            // at or below the value identifies the owner, and for the owning lane the last slab in which
+            // its own group qualified is the owning slab.
+            uint64_t inc[IT];
 #pragma unroll
             for (int k = 0; k < IT; k++) {
-                uint64_t gsum = 0;
+                uint64_t a = 0;
 #pragma unroll
-                for (int e = 0; e < VEC; e++) gsum += q[k * VEC + e];
-                uint64_t tot = warp_sum(gsum);
-                int g0 = gbeg + k * 32;
-                if (g0 < gend && lowpos(lq::cum_of(Ck, (uint32_t)(g0 * VEC), sc), w) <= xr) {
-                    ksel = k;
-                    Csel = Ck;
-                }
-                Ck += tot;
+                for (int e = 0; e < VEC; e++) a += q[k * VEC + e];
+                inc[k] = a;
             }
-            // ---- lane level inside slab ksel
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+                for (int k = 0; k < IT; k++) {
+                    uint64_t v = __shfl_up_sync(0xffffffffu, inc[k], o);
+                    if (lane >= o) inc[k] += v;
+                }
+            }
+            uint64_t base = Cb, C = 0;
+            int cnt = 0, ksel = 0;
             uint32_t qe[VEC];
-            uint64_t gsum = 0;
+#pragma unroll
+            for (int e = 0; e < VEC; e++) qe[e] = 0;
 #pragma unroll
             for (int k = 0; k < IT; k++) {
-                if (k == ksel) {
+                uint64_t a = 0;
+#pragma unroll
+                for (int e = 0; e < VEC; e++) a += q[k * VEC + e];
+                const uint64_t Cg = base + inc[k] - a;
+                base += __shfl_sync(0xffffffffu, inc[k], 31);
+                const int gk = gbeg + k * 32 + lane;
+                const bool ok = gk < gend && cum_le(lq::cum_of(Cg, (uint32_t)(gk * VEC), sc), xr, w);
+                cnt += __popc(__ballot_sync(0xffffffffu, ok));
+                if (ok) {
+                    C = Cg;
+                    ksel = k;
 #pragma unroll
                     for (int e = 0; e < VEC; e++) qe[e] = q[k * VEC + e];
                 }
             }
+            const int j = cnt - 1;  // ordinal of the owning group in (slab, lane) order
+            if (lane == (j & 31)) {
+                // ---- element level (one lane)
+                const int g = gbeg + ksel * 32 + lane;
+                int sym = g * VEC;
+                uint64_t Cs = C, Ce = C;
+                uint32_t qsym = qe[0];
 #pragma unroll
-            for (int e = 0; e < VEC; e++) gsum += qe[e];
-            const int g = gbeg + ksel * 32 + lane;
-            uint64_t inc = warp_incl_scan(gsum, lane);
-            uint64_t C = Csel + inc - gsum;
-            bool ok = g < gend && lowpos(lq::cum_of(C, (uint32_t)(g * VEC), sc), w) <= xr;
-            unsigned ball = __ballot_sync(0xffffffffu, ok);
-            int lsel = 31 - __clz((int)ball);
-            if (lane != lsel) continue;
-            // ---- element level (one lane)
-            int sym = g * VEC;
-            uint64_t Cs = C, Ce = C;
-#pragma unroll
-            for (int e = 1; e < VEC; e++) {
-                Ce += qe[e - 1];
-                if (lowpos(lq::cum_of(Ce, (uint32_t)(g * VEC + e), sc), w) <= xr) {
-                    sym = g * VEC + e;
-                    Cs = Ce;
+                for (int e = 1; e < VEC; e++) {
+                    Ce += qe[e - 1];
+                    if (cum_le(lq::cum_of(Ce, (uint32_t)(g * VEC + e), sc), xr, w)) {
+                        sym = g * VEC + e;
+                        Cs = Ce;
+                        qsym = qe[e];
+                    }
+                }
+                const uint32_t lo = lq::cum_of(Cs, (uint32_t)sym, sc);
+                const uint32_t hi = (sym == V - 1) ? 0u : lq::cum_of(Cs + qsym, (uint32_t)sym + 1, sc);
+                // ---- A_from_bin.emit_symbol + emit_bit loop (arith_code.py:278-298)
+                int64_t nl = dec.low, nh = dec.high;
+                const int64_t value = dec.value;
+                coder::ac_narrow32(nl, nh, lo, hi);
+                const int64_t off = value - nl;  // the value stays inside [nl, nh]
+                const int k = coder::renorm_count((uint64_t)(nh - nl + 1), P);
+                coder::renorm_apply(nl, nh, P, k);
+                // next k bits from the 128-bit window (k <= 60, window offset < 64)
+                const uint64_t pos = dec.pos;
+                const uint64_t hi64 = dec.win_hi, lo64 = dec.win_lo, wb = dec.win_byte;
+                const int o = (int)(pos - (wb << 3));
+                const uint64_t comb = o ? ((hi64 << o) | (lo64 >> (64 - o))) : hi64;
+                const uint64_t nb = k ? (comb >> (64 - k)) : 0;
+                const int64_t nv = nl + (off << k) + (int64_t)nb;
+                syms[s * sym_stride + t] = sym;
+                if (last) {
+                    state[s].low = nl;
+                    state[s].high = nh;
+                    state[s].value = nv;
+                    state[s].pos = pos + (uint64_t)k;
+                } else {
+                    dec.low = nl;
+                    dec.high = nh;
+                    dec.value = nv;
+                    dec.pos = pos + (uint64_t)k;
+                    if (o + k >= 64) {  // slide the window by 8 bytes
+                        dec.win_hi = lo64;
+                        dec.win_byte = wb + 8;
+                        dec.win_lo = load_be64(bytes + dec.data_off, dec.nbytes, wb + 16);
+                    }
                 }
             }
-            uint32_t qsym = qe[0];
-#pragma unroll
-            for (int e = 1; e < VEC; e++)
-                if (sym == g * VEC + e) qsym = qe[e];
-            const uint32_t lo = lq::cum_of(Cs, (uint32_t)sym, sc);
-            const uint32_t hi = (sym == V - 1) ? 0u : lq::cum_of(Cs + qsym, (uint32_t)sym + 1, sc);
-            // ---- A_from_bin.emit_symbol + emit_bit loop (arith_code.py:278-298)
-            int64_t nl = l, nh = h;
-            coder::ac_narrow32(nl, nh, lo, hi);
-            const int64_t off = sm.dec.value - nl;  // value stays inside [nl, nh]
-            const int k = coder::renorm_count((uint64_t)(nh - nl + 1), P);
-            coder::renorm_apply(nl, nh, P, k);
-            const uint64_t pos = sm.dec.pos;
-            const uint64_t nb = coder::read_bits(data, nbytes, pos, k);
-            sm.dec.low = nl;
-            sm.dec.high = nh;
-            sm.dec.value = nl + (off << k) + (int64_t)nb;
-            sm.dec.pos = pos + (uint64_t)k;
-            syms[s * sym_stride + t] = sym;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            state[s].low = sm.dec.low;
-            state[s].high = sm.dec.high;
-            state[s].value = sm.dec.value;
-            state[s].pos = sm.dec.pos;
-            state[s].status = sm.dec.status;
+            __syncwarp();
         }
     }
 }
@@ -365,18 +667,37 @@ static int grid_for(int64_t units) {
     return (int)(units < sms ? (units > 0 ? units : 1) : sms);
 }
 
-static bool vec4_ok(const float* p, int V, int64_t s0, int64_t s1) {
-    return (V % 4 == 0) && ((((uintptr_t)p) & 15) == 0) && (s0 % 4 == 0) && (s1 % 4 == 0);
+// 0: scalar LDG (any alignment), 1: 128-bit LDG, 2 / 4 / 8: TMA bulk ring with that many chunks per row
+// (default 2 when rows are 16-byte aligned; LAC_NO_TMA=1 and LAC_TMA_CHUNKS=n are measurement switches)
+static int path_for(const float* p, int V, int64_t s0, int64_t s1) {
+    bool v4 = (V % 4 == 0) && ((((uintptr_t)p) & 15) == 0) && (s0 % 4 == 0) && (s1 % 4 == 0);
+    if (!v4) return 0;
+    static const bool no_tma = getenv("LAC_NO_TMA") != nullptr;
+    if (no_tma) return 1;
+    static const int nch = getenv("LAC_TMA_CHUNKS") ? atoi(getenv("LAC_TMA_CHUNKS")) : 2;
+    return (nch == 4 || nch == 8) ? nch : 2;
+}
+
+template <typename K, typename... A>
+static cudaError_t launch_tma(K kernel, int ring_bytes, int grid, cudaStream_t st, A... args) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, kThreads, ring_bytes, st>>>(args...);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_lookup(const float* logits, int64_t rows, int V, int64_t row_stride, const int32_t* syms,
                           uint32_t* pairs, uint32_t* status, cudaStream_t st) {
     if (rows == 0) return cudaSuccess;
     int grid = grid_for(rows);
-    if (vec4_ok(logits, V, row_stride, 0))
-        lookup_kernel<4><<<grid, kThreads, 0, st>>>(logits, rows, V, row_stride, syms, pairs, status);
-    else
-        lookup_kernel<1><<<grid, kThreads, 0, st>>>(logits, rows, V, row_stride, syms, pairs, status);
+    const RowParams rp{logits, rows, 1, row_stride, 0, nullptr};
+    switch (path_for(logits, V, row_stride, 0)) {
+        case 2: return launch_tma(lookup_kernel<4, true, 2>, Ring<2>::kRingBytes, grid, st, rp, V, syms, pairs, status);
+        case 4: return launch_tma(lookup_kernel<4, true, 4>, Ring<4>::kRingBytes, grid, st, rp, V, syms, pairs, status);
+        case 8: return launch_tma(lookup_kernel<4, true, 8>, Ring<8>::kRingBytes, grid, st, rp, V, syms, pairs, status);
+        case 1: lookup_kernel<4, false, 8><<<grid, kThreads, 0, st>>>(rp, V, syms, pairs, status); break;
+        default: lookup_kernel<1, false, 8><<<grid, kThreads, 0, st>>>(rp, V, syms, pairs, status);
+    }
     return cudaGetLastError();
 }
 
@@ -384,10 +705,14 @@ cudaError_t launch_build(const float* logits, int64_t rows, int V, int64_t row_s
                          cudaStream_t st) {
     if (rows == 0) return cudaSuccess;
     int grid = grid_for(rows);
-    if (vec4_ok(logits, V, row_stride, 0))
-        build_kernel<4><<<grid, kThreads, 0, st>>>(logits, rows, V, row_stride, cum);
-    else
-        build_kernel<1><<<grid, kThreads, 0, st>>>(logits, rows, V, row_stride, cum);
+    const RowParams rp{logits, rows, 1, row_stride, 0, nullptr};
+    switch (path_for(logits, V, row_stride, 0)) {
+        case 2: return launch_tma(build_kernel<4, true, 2>, Ring<2>::kRingBytes, grid, st, rp, V, cum);
+        case 4: return launch_tma(build_kernel<4, true, 4>, Ring<4>::kRingBytes, grid, st, rp, V, cum);
+        case 8: return launch_tma(build_kernel<4, true, 8>, Ring<8>::kRingBytes, grid, st, rp, V, cum);
+        case 1: build_kernel<4, false, 8><<<grid, kThreads, 0, st>>>(rp, V, cum); break;
+        default: build_kernel<1, false, 8><<<grid, kThreads, 0, st>>>(rp, V, cum);
+    }
     return cudaGetLastError();
 }
 
@@ -397,12 +722,14 @@ cudaError_t launch_decode(const float* logits, int64_t n_streams, int64_t T, int
                           int P, cudaStream_t st) {
     if (n_streams == 0 || T == 0) return cudaSuccess;
     int grid = grid_for(n_streams);
-    if (vec4_ok(logits, V, stream_stride, tok_stride))
-        decode_kernel<4><<<grid, kThreads, 0, st>>>(logits, n_streams, T, stream_stride, tok_stride, V, ntok,
-                                                    state, bytes, offsets, syms, sym_stride, P);
-    else
-        decode_kernel<1><<<grid, kThreads, 0, st>>>(logits, n_streams, T, stream_stride, tok_stride, V, ntok,
-                                                    state, bytes, offsets, syms, sym_stride, P);
+    const RowParams rp{logits, n_streams, T, stream_stride, tok_stride, ntok};
+    switch (path_for(logits, V, stream_stride, tok_stride)) {
+        case 2: return launch_tma(decode_kernel<4, true, 2>, Ring<2>::kRingBytes, grid, st, rp, V, state, bytes, offsets, syms, sym_stride, P);
+        case 4: return launch_tma(decode_kernel<4, true, 4>, Ring<4>::kRingBytes, grid, st, rp, V, state, bytes, offsets, syms, sym_stride, P);
+        case 8: return launch_tma(decode_kernel<4, true, 8>, Ring<8>::kRingBytes, grid, st, rp, V, state, bytes, offsets, syms, sym_stride, P);
+        case 1: decode_kernel<4, false, 8><<<grid, kThreads, 0, st>>>(rp, V, state, bytes, offsets, syms, sym_stride, P); break;
+        default: decode_kernel<1, false, 8><<<grid, kThreads, 0, st>>>(rp, V, state, bytes, offsets, syms, sym_stride, P);
+    }
     return cudaGetLastError();
 }
 

@@ -318,13 +318,19 @@ __global__ void acs_tables_encode_kernel(const uint64_t* __restrict__ cdf, int V
         int k = coder::renorm_count((uint64_t)(high - low + 1), P);
         bw.append(coder::renorm_apply(low, high, P, k), k);
     }
-    if (finish && !(bw.status & (LAC_ST_TABLE | LAC_ST_SYMBOL))) {
-        // flush_compress, arithmetic_coding.py:52-58: step(1, 2, 3), drain the carry buffer, reset
+    if (finish == 1 && !(bw.status & (LAC_ST_TABLE | LAC_ST_SYMBOL))) {
+        // flush_compress, arithmetic_coding.py:52-58: step(1, 2, 3), drain the carry buffer, reset.
+        // Bit-exact with the reference, but the bits do not pin the final region (DESIGN.md
+        // section 6): the last tokens may be undecodable by ANY decoder.
         coder::acs_narrow(low, high, 1, 2, 3);
         int k = coder::renorm_count((uint64_t)(high - low + 1), P);
         bw.append(coder::renorm_apply(low, high, P, k), k);
         low = 0;
         high = (1ll << P) - 1;
+    } else if (finish == 2 && !(bw.status & (LAC_ST_TABLE | LAC_ST_SYMBOL))) {
+        // safe termination: shortest bit string whose every continuation stays inside [low, high]
+        // (A_to_bin.flush, arith_code.py:185-194) -- always decodable
+        coder::ac_flush(low, high, P, bw);
     }
     bw.close();
     state[s].low = low;

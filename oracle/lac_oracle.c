@@ -443,7 +443,9 @@ int orc_acs_decode(int prec, const uint64_t *cdf, int64_t stride, int64_t ntab, 
 /* ================================================================== */
 #define LQ_LOG2E 0x3FB8AA3Bu
 #define LQ_MAGIC 0x4B400000u /* 1.5 * 2^23 */
-static const uint32_t LQ_C[5] = {0x4f000000u, 0x4eb17096u, 0x4df601bcu, 0x4ce4fe23u, 0x4b9d0163u};
+/* minimax 2^f on [-0.5, 0.5], degree 3, scaled by 2^22: c1..c3 (max rel. error 1.02e-4); the constant
+ * term 2^22 is folded into MAGIC */
+static const uint32_t LQ_C[4] = {0x4a800000u, 0x4a317afdu, 0x49780626u, 0x4861510cu};
 static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
@@ -453,23 +455,27 @@ static inline float lq_max(float a, float b) {
     if (b != b) return a;
     return a > b ? a : b;
 }
-/* q_i = floor(2^((x_i - m) * log2 e) * 2^31) per DESIGN.md section 3 steps 2-4. */
+/* q_i ~ 2^((x_i - m) * log2 e) * 2^31 per DESIGN.md section 3 steps 2-4 (no float->int conversion
+ * instruction anywhere: integers are read out of float mantissas):
+ *   d = x - m                      (<= 0, or NaN / -inf)
+ *   t = fma(d, log2e, MAGIC)       MAGIC = 1.5 * 2^23: the low mantissa bits of t hold n = rne(d*log2e)
+ *   sh = MAGIC_BITS - bits(t)      (unsigned; = -n for n in [-31, 0], >= 32 for everything else incl. NaN)
+ *   f = fma(d, log2e, MAGIC - t)   residual in [-0.5, 0.5], single rounding
+ *   z = fma(fma(fma(c3, f, c2), f, c1), f, MAGIC)                = 1.5*2^23 + 2^22 (2^f - 1), ulp 1
+ *   P = bits(z) & 0x7FFFFF         = rne(2^22 * 2^f) in [2^21.5, 2^22.5]
+ *   q = sh >= 32 ? 0 : (P << 9) >> sh */
 static inline uint32_t lq_q(float x, float m) {
     float d = x - m;
-    float y0 = d * u2f(LQ_LOG2E);
-    float y = lq_max(y0, -64.0f);
-    float t = y + u2f(LQ_MAGIC);
-    int32_t n = (int32_t)(f2u(t) - LQ_MAGIC);      /* round-to-nearest-even(y), in [-64, 0] */
-    float r = t - u2f(LQ_MAGIC);
-    float f = y - r;
-    float p = u2f(LQ_C[4]);
-    p = fmaf(p, f, u2f(LQ_C[3]));
+    float t = fmaf(d, u2f(LQ_LOG2E), u2f(LQ_MAGIC));
+    uint32_t sh = LQ_MAGIC - f2u(t);
+    if (sh >= 32) return 0u;
+    float rn = u2f(LQ_MAGIC) - t;
+    float f = fmaf(d, u2f(LQ_LOG2E), rn);
+    float p = u2f(LQ_C[3]);
     p = fmaf(p, f, u2f(LQ_C[2]));
     p = fmaf(p, f, u2f(LQ_C[1]));
-    p = fmaf(p, f, u2f(LQ_C[0]));
-    uint32_t P = (uint32_t)p;                       /* cvt.rzi.u32.f32; p in (2^30.4, 2^31.6) */
-    uint32_t sh = (uint32_t)(-n);
-    return sh >= 32 ? 0u : (P >> sh);
+    float z = fmaf(p, f, u2f(LQ_MAGIC));
+    return (f2u(z) << 9) >> sh;
 }
 static inline float lq_rowmax(const float *x, int V) {
     float m = u2f(0xFF800000u); /* -inf */
@@ -478,12 +484,16 @@ static inline float lq_rowmax(const float *x, int V) {
 }
 typedef struct { uint64_t Q; uint32_t R; int s; } lq_scale;
 static inline lq_scale lq_make_scale(uint64_t Q, int V) {
+    /* s = bitlen(Q) - 1 (>= 31 whenever Q != 0: the row maximum contributes q = 2^31);
+     * D = (Q >> (s - 31)) + 1 in (2^31, 2^32];  R = floor((M << 31) / D) <= M * 2^s / Q,
+     * so sum_i floor(q_i-prefix scaling) never exceeds M = 2^32 - V. */
     lq_scale k = {Q, 0, 0};
-    if (Q == 0) return k;
+    if (Q < ((uint64_t)1 << 31)) return k; /* only the degenerate Q == 0 row (no finite maximum) */
     int b = 64 - __builtin_clzll(Q);
     k.s = b - 1;
-    u128 M = ((u128)1 << 32) - (u128)V;
-    k.R = (uint32_t)((M << k.s) / Q);
+    uint64_t M = ((uint64_t)1 << 32) - (uint64_t)V;
+    uint64_t D = (Q >> (k.s - 31)) + 1;
+    k.R = (uint32_t)((M << 31) / D);
     return k;
 }
 static inline uint32_t lq_cum(uint64_t C, uint32_t i, lq_scale k) {

