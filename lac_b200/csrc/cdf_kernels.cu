@@ -20,6 +20,7 @@
 //            DECODE: 8 interleaved lane scans + ballots locate the 4-element group in the owner warp,
 //                    one lane finishes the search and runs the A_from_bin state update.
 // The integer formulation (lq32.cuh) makes the result independent of this decomposition.
+#include <climits>
 #include <cstdint>
 #include <cstdlib>
 #include <cuda_runtime.h>
@@ -116,25 +117,26 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
     return r;
 }
 
-// Two q values at once: exactly lq::q_of's operations (explicit FMAs -- ptxas contracts packed
-// mul+add pairs on its own, so the spec fuses them by definition), two lanes per instruction:
-// FADD2, FFMA2, FADD2, FFMA2, 3 x FFMA2 per pair, then shl / funnel-shift per element.  No F2I.
-__device__ __forceinline__ void q_of2(float xa, float xb, uint64_t m2, uint32_t& qa, uint32_t& qb) {
+// Two elements per instruction (FFMA2 / FADD2), exactly lq::q_of's operations (explicit FMAs: ptxas
+// contracts packed mul+add pairs on its own, so the spec fuses them by definition):
+// FFMA2, FADD2, FFMA2, 3 x FFMA2 per pair, then sub / shl / funnel-shift per element.  No F2I.
+__device__ __forceinline__ void q_of2(float xa, float xb, uint32_t nref, uint32_t& qa, uint32_t& qb) {
     const uint64_t L2 = pk2(lq::log2e(), lq::log2e());
     const uint64_t MG = pk2(lq::magic(), lq::magic());
-    uint64_t d = sub2(pk2(xa, xb), m2);
-    uint64_t t = fma2(d, L2, MG);
+    const uint64_t MZ = pk2(lq::magicz(), lq::magicz());
+    const uint64_t x2 = pk2(xa, xb);
+    uint64_t t = fma2(x2, L2, MG);
     uint64_t rn = sub2(MG, t);
-    uint64_t f = fma2(d, L2, rn);
+    uint64_t f = fma2(x2, L2, rn);
     uint64_t p = pk2(__uint_as_float(lq::kC3), __uint_as_float(lq::kC3));
     p = fma2(p, f, pk2(__uint_as_float(lq::kC2), __uint_as_float(lq::kC2)));
     p = fma2(p, f, pk2(__uint_as_float(lq::kC1), __uint_as_float(lq::kC1)));
-    uint64_t z = fma2(p, f, MG);
+    uint64_t z = fma2(p, f, MZ);
     float za, zb, ta, tb;
     upk2(z, za, zb);
     upk2(t, ta, tb);
-    qa = __funnelshift_rc(__float_as_uint(za) << 9, 0u, 0x4B400000u - __float_as_uint(ta));
-    qb = __funnelshift_rc(__float_as_uint(zb) << 9, 0u, 0x4B400000u - __float_as_uint(tb));
+    qa = __funnelshift_rc(__float_as_uint(za) << 7, 0u, nref - __float_as_uint(ta));
+    qb = __funnelshift_rc(__float_as_uint(zb) << 7, 0u, nref - __float_as_uint(tb));
 }
 
 // ------------------------------------------------------------------ warp collectives (REDUX where possible)
@@ -143,7 +145,6 @@ __device__ __forceinline__ int f2ord(float f) {  // order-preserving float -> in
     return b ^ ((b >> 31) & 0x7fffffff);
 }
 __device__ __forceinline__ float ord2f(int o) { return __int_as_float(o ^ ((o >> 31) & 0x7fffffff)); }
-__device__ __forceinline__ float warp_max(float v) { return ord2f(__reduce_max_sync(0xffffffffu, f2ord(v))); }
 // sum over the warp of values < 2^48: three 16-bit limbs through REDUX.SUM
 __device__ __forceinline__ uint64_t warp_sum48(uint64_t v) {
     uint32_t a = __reduce_add_sync(0xffffffffu, (uint32_t)v & 0xffffu);
@@ -174,7 +175,7 @@ struct DecShared {
 struct Ctl {
     uint64_t full[kMaxChunks];  // TMA chunk landed
     uint64_t done;              // row-level bookkeeping published (phase = row parity)
-    float red_max[2][kWarps];   // per-warp maxima, double-buffered by row parity
+    int red_max[2][kWarps];     // per-warp maxima (order-preserving ints), double-buffered by row parity
     uint64_t wsum[kWarps];      // per-warp totals of q
     uint64_t pref[kWarps];      // exclusive prefix of wsum   } written once per row by the last warp
     uint64_t Q;                 // sum of wsum                } to finish phase B, then `done` flips
@@ -219,185 +220,197 @@ struct RowSeq {
     }
 };
 
-// ------------------------------------------------------------------ row engine: staging + phases A, B + finish
+// ------------------------------------------------------------------ row engine: staging + passes + finish
+// File-scope shared objects have compile-time addresses, and everything about the row geometry is
+// recomputed from (warp, V) on demand, so the engine keeps ONE register of state (the row counter):
+// with 32 row elements per thread and a 64-register budget nothing else may stay live in the hot loop.
+__shared__ Ctl g_ctl;
+extern __shared__ __align__(128) unsigned char g_ring[];
+
 template <int VEC, bool TMA, int NCH>
 struct RowEngine {
     static constexpr int IT = kPerThread / VEC;
     static constexpr int kWarpsPerChunk = Ring<NCH>::kWarpsPerChunk;
     static constexpr int kSlotBytes = Ring<NCH>::kSlotBytes;
-    int warp, lane, V, G, gbeg, gend;
-    int cg0;
-    uint32_t cbytes, it;
-    Ctl* ctl;
-    unsigned char* ring;
-    __device__ __forceinline__ int chunk() const { return warp / kWarpsPerChunk; }
-    __device__ __forceinline__ bool leader() const { return (warp % kWarpsPerChunk == 0) && lane == 0; }
-    __device__ __forceinline__ unsigned char* slot() const { return ring + chunk() * kSlotBytes; }
+    uint32_t it;
 
-    __device__ void setup(int V_, Ctl* c, unsigned char* ring_) {
-        warp = threadIdx.x >> 5;
-        lane = threadIdx.x & 31;
-        V = V_;
-        G = V / VEC;
-        gbeg = (int)(((int64_t)warp * G) / kWarps);
-        gend = (int)(((int64_t)(warp + 1) * G) / kWarps);
-        ctl = c;
-        ring = ring_;
+    static __device__ __forceinline__ int warp() { return threadIdx.x >> 5; }
+    static __device__ __forceinline__ int lane() { return threadIdx.x & 31; }
+    static __device__ __forceinline__ int groups(int V) { return V / VEC; }
+    static __device__ __forceinline__ int seg_begin(int w, int V) { return (int)(((int64_t)w * groups(V)) / kWarps); }
+    static __device__ __forceinline__ int gbeg(int V) { return seg_begin(warp(), V); }
+    static __device__ __forceinline__ int gend(int V) { return seg_begin(warp() + 1, V); }
+    static __device__ __forceinline__ int chunk() { return warp() / kWarpsPerChunk; }
+    static __device__ __forceinline__ int cg0(int V) { return seg_begin(chunk() * kWarpsPerChunk, V); }
+    static __device__ __forceinline__ uint32_t cbytes(int V) {
+        return (uint32_t)(seg_begin((chunk() + 1) * kWarpsPerChunk, V) - cg0(V)) * 16u;
+    }
+    static __device__ __forceinline__ bool leader() { return (threadIdx.x & (32 * kWarpsPerChunk - 1)) == 0; }
+    static __device__ __forceinline__ unsigned char* slot() { return g_ring + chunk() * kSlotBytes; }
+
+    __device__ void setup() {
         it = 0;
-        cg0 = 0;
-        cbytes = 0;
-        if (TMA) {
-            cg0 = (int)(((int64_t)(chunk() * kWarpsPerChunk) * G) / kWarps);
-            int cg1 = (int)(((int64_t)((chunk() + 1) * kWarpsPerChunk) * G) / kWarps);
-            cbytes = (uint32_t)(cg1 - cg0) * 16u;
-        }
         if (threadIdx.x == 0) {
-            c->arrive = 0;
-            for (int i = 0; i < NCH; i++) mbar_init(&ctl->full[i], 1);
-            mbar_init(&ctl->done, 1);
+            g_ctl.arrive = 0;
+            for (int i = 0; i < NCH; i++) mbar_init(&g_ctl.full[i], 1);
+            mbar_init(&g_ctl.done, 1);
             fence_mbar_init();
         }
         __syncthreads();
     }
-    __device__ __forceinline__ void issue(const float* row) {  // chunk leader: arm + bulk copy of this chunk
-        if (TMA && leader() && cbytes) {
-            mbar_expect_tx(&ctl->full[chunk()], cbytes);
-            tma_load_1d(slot(), row + 4 * (int64_t)cg0, cbytes, &ctl->full[chunk()], evict_first_policy());
+    static __device__ __forceinline__ void issue(const float* row, int V) {  // chunk leader: arm + bulk copy
+        if (TMA && leader()) {
+            const uint32_t nb = cbytes(V);
+            if (nb) {
+                mbar_expect_tx(&g_ctl.full[chunk()], nb);
+                tma_load_1d(slot(), row + 4 * (int64_t)cg0(V), nb, &g_ctl.full[chunk()], evict_first_policy());
+            }
         }
     }
 
-    // Phases A and B for `row`; `next_row` (or nullptr) is prefetched as soon as this row has left shared
-    // memory.  On return q[] holds this thread's q values; the row-level results (ctl->pref, Q, R, s,
-    // owner) are valid once wait_done() returns.
-    __device__ __forceinline__ void reduce(const float* __restrict__ row, const float* next_row,
+    // One row: stage it into registers, phase A (maximum), the row's single block barrier, phase B (q, sums).
+    // `next_row` (or nullptr) is prefetched as soon as this row has left shared memory.  On return q[] holds
+    // this thread's final q values; the row-level results (g_ctl.pref, Q, R, s, owner) are valid once
+    // wait_done() returns.
+    __device__ __forceinline__ void reduce(const float* __restrict__ row, const float* next_row, int V,
                                            uint32_t (&q)[kPerThread], const DecShared* dec = nullptr) {
         float x[kPerThread];
-        if (TMA) {
-            if (cbytes) mbar_wait(&ctl->full[chunk()], it & 1);
-            const unsigned char* sl = slot();
+        {
+            const int gb = gbeg(V), ge = gend(V), ln = lane();
+            if (TMA) {
+                if (cbytes(V)) mbar_wait(&g_ctl.full[chunk()], it & 1);
+                const unsigned char* sl = slot() - (size_t)cg0(V) * 16;
 #pragma unroll
-            for (int k = 0; k < IT; k++) {
-                int g = gbeg + k * 32 + lane;
-                float4 v = make_float4(lq::neg_inf(), lq::neg_inf(), lq::neg_inf(), lq::neg_inf());
-                if (g < gend) v = *reinterpret_cast<const float4*>(sl + (size_t)(g - cg0) * 16);
-                x[4 * k + 0] = v.x;
-                x[4 * k + 1] = v.y;
-                x[4 * k + 2] = v.z;
-                x[4 * k + 3] = v.w;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < IT; k++) {
-                int g = gbeg + k * 32 + lane;
-                if (VEC == 4) {
+                for (int k = 0; k < IT; k++) {
+                    int g = gb + k * 32 + ln;
                     float4 v = make_float4(lq::neg_inf(), lq::neg_inf(), lq::neg_inf(), lq::neg_inf());
-                    if (g < gend) v = ldg_stream4(row + 4 * (int64_t)g);
+                    if (g < ge) v = *reinterpret_cast<const float4*>(sl + (size_t)g * 16);
                     x[4 * k + 0] = v.x;
                     x[4 * k + 1] = v.y;
                     x[4 * k + 2] = v.z;
                     x[4 * k + 3] = v.w;
-                } else {
-                    x[k] = g < gend ? ldg_stream1(row + g) : lq::neg_inf();
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < IT; k++) {
+                    int g = gb + k * 32 + ln;
+                    if (VEC == 4) {
+                        float4 v = make_float4(lq::neg_inf(), lq::neg_inf(), lq::neg_inf(), lq::neg_inf());
+                        if (g < ge) v = ldg_stream4(row + 4 * (int64_t)g);
+                        x[4 * k + 0] = v.x;
+                        x[4 * k + 1] = v.y;
+                        x[4 * k + 2] = v.z;
+                        x[4 * k + 3] = v.w;
+                    } else {
+                        x[k] = g < ge ? ldg_stream1(row + g) : lq::neg_inf();
+                    }
                 }
             }
         }
+        // phase A: row maximum (fmaxf drops NaNs; the running value starts at -inf, so it is never NaN)
         float m = lq::neg_inf();
 #pragma unroll
-        for (int i = 0; i < kPerThread; i++) m = lq::vmax(m, x[i]);
+        for (int i = 0; i < kPerThread; i++) m = fmaxf(m, x[i]);
         if (TMA) {
-            // every thread's max depends on all its shared-memory loads, so after this barrier the
-            // chunk is fully in registers and the slot can be overwritten by the next row
+            // m depends on every shared-memory load of this thread, so after this barrier the chunk is
+            // fully in registers and the slot can be overwritten by the next row
             named_bar_sync(1 + chunk(), 32 * kWarpsPerChunk);
             if (next_row) {
                 if (leader()) fence_proxy_async();
-                issue(next_row);
+                issue(next_row, V);
             }
         }
-        m = warp_max(m);
-        float* red = ctl->red_max[it & 1];
-        if (lane == 0) red[warp] = m;
+        const int mw = __reduce_max_sync(0xffffffffu, f2ord(m));
+        int* red = g_ctl.red_max[it & 1];
+        if (lane() == 0) red[warp()] = mw;
         __syncthreads();  // the only block-wide barrier of the row
-        m = warp_max(red[lane]);
-        const uint64_t m2 = pk2(m, m);
+        const int nref = lq::ref_of_max(ord2f(__reduce_max_sync(0xffffffffu, red[lane()])));
+        // phase B: q against the row-wide reference, uint32 sums per 4 elements (4 q < 2^31.5), uint64 per lane
+        // (a degenerate row -- no finite maximum, +inf, out of range -- gets a reference that pushes every
+        // shift count past 31, i.e. q = 0 everywhere and the uniform table, without a second code path)
+        const uint32_t nref_u = lq::ref_valid(nref) ? (uint32_t)nref : 0xFFFFFFFFu;
         uint64_t lane_sum = 0;
 #pragma unroll
-        for (int i = 0; i < kPerThread; i += 2) {
-            q_of2(x[i], x[i + 1], m2, q[i], q[i + 1]);
-            lane_sum += q[i];
-            lane_sum += q[i + 1];
+        for (int i = 0; i < kPerThread; i += 4) {
+            q_of2(x[i], x[i + 1], nref_u, q[i], q[i + 1]);
+            q_of2(x[i + 2], x[i + 3], nref_u, q[i + 2], q[i + 3]);
+            lane_sum += (q[i] + q[i + 1]) + (q[i + 2] + q[i + 3]);
         }
         const uint64_t ws = warp_sum48(lane_sum);
         uint32_t prev = 0;
-        if (lane == 0) {
-            ctl->wsum[warp] = ws;
+        if (lane() == 0) {
+            g_ctl.wsum[warp()] = ws;
             fence_acq_rel_cta();
-            prev = atomicAdd(&ctl->arrive, 1u);
+            prev = atomicAdd(&g_ctl.arrive, 1u);
         }
         prev = __shfl_sync(0xffffffffu, prev, 0);
-        if (prev == kWarps - 1) {  // last warp of the row: every wsum[] is visible
-            fence_acq_rel_cta();
-            const uint64_t v = *reinterpret_cast<volatile uint64_t*>(&ctl->wsum[lane]);
-            const uint64_t inc = warp_incl_scan(v, lane);
-            const uint64_t Q = __shfl_sync(0xffffffffu, inc, 31);
-            const uint64_t exc = inc - v;
-            ctl->pref[lane] = exc;
-            lq::Scale sc;
-            sc.Q = Q;
-            sc.R = 0;
-            sc.s = 0;
-            if (lane == 0) sc = lq::make_scale(Q, V);
-            sc.R = __shfl_sync(0xffffffffu, sc.R, 0);
-            sc.s = __shfl_sync(0xffffffffu, sc.s, 0);
-            if (dec) {  // lane w tests warp w's segment start: the owner is the last non-empty one at or below the value
-                const int gb = (int)(((int64_t)lane * G) / kWarps), ge = (int)(((int64_t)(lane + 1) * G) / kWarps);
-                const uint64_t w = (uint64_t)(dec->high - dec->low + 1), xr = (uint64_t)(dec->value - dec->low);
-                const bool ok = gb < ge && coder::scale32_ceil(lq::cum_of(exc, (uint32_t)(gb * VEC), sc), w) <= xr;
-                const unsigned ball = __ballot_sync(0xffffffffu, ok);
-                if (lane == 0) ctl->owner = 31 - __clz((int)ball);
-            }
-            __syncwarp();
-            if (lane == 0) {
-                ctl->Q = Q;
-                ctl->R = sc.R;
-                ctl->s = sc.s;
-                ctl->arrive = 0;
-                mbar_arrive(&ctl->done);  // release: publishes everything above
-            }
-        }
+        if (prev == kWarps - 1) finish_row(V, dec);  // last warp of the row: every wsum[] is visible
         it++;
     }
-    // Block until the row-level results of the row just reduce()d are published.
-    __device__ __forceinline__ void wait_done() const { mbar_wait(&ctl->done, (it - 1) & 1); }
-    __device__ __forceinline__ lq::Scale scale() const {
+
+    // Row-level bookkeeping, run by exactly one warp per row.
+    static __device__ __noinline__ void finish_row(int V, const DecShared* dec) {
+        const int ln = lane();
+        fence_acq_rel_cta();
+        const uint64_t v = *reinterpret_cast<volatile uint64_t*>(&g_ctl.wsum[ln]);
+        const uint64_t inc = warp_incl_scan(v, ln);
+        const uint64_t Q = __shfl_sync(0xffffffffu, inc, 31);
+        const uint64_t exc = inc - v;
+        g_ctl.pref[ln] = exc;
         lq::Scale sc;
-        sc.Q = ctl->Q;
-        sc.R = ctl->R;
-        sc.s = ctl->s;
+        sc.Q = Q;
+        sc.R = 0;
+        sc.s = 0;
+        if (ln == 0) sc = lq::make_scale(Q, V);
+        sc.R = __shfl_sync(0xffffffffu, sc.R, 0);
+        sc.s = __shfl_sync(0xffffffffu, sc.s, 0);
+        if (dec) {  // lane w tests warp w's segment start: the owner is the last non-empty one at or below the value
+            const int gb = seg_begin(ln, V), ge = seg_begin(ln + 1, V);
+            const uint64_t w = (uint64_t)(dec->high - dec->low + 1), xr = (uint64_t)(dec->value - dec->low);
+            const bool ok = gb < ge && coder::scale32_ceil(lq::cum_of(exc, (uint32_t)(gb * VEC), sc), w) <= xr;
+            const unsigned ball = __ballot_sync(0xffffffffu, ok);
+            if (ln == 0) g_ctl.owner = 31 - __clz((int)ball);
+        }
+        __syncwarp();
+        if (ln == 0) {
+            g_ctl.Q = Q;
+            g_ctl.R = sc.R;
+            g_ctl.s = sc.s;
+            g_ctl.arrive = 0;
+            mbar_arrive(&g_ctl.done);  // release: publishes everything above
+        }
+    }
+    // Block until the row-level results of the row just reduce()d are published.
+    __device__ __forceinline__ void wait_done() const { mbar_wait(&g_ctl.done, (it - 1) & 1); }
+    static __device__ __forceinline__ lq::Scale scale() {
+        lq::Scale sc;
+        sc.Q = g_ctl.Q;
+        sc.R = g_ctl.R;
+        sc.s = g_ctl.s;
         return sc;
     }
 };
-
-extern __shared__ __align__(128) unsigned char g_ring[];
 
 // ------------------------------------------------------------------ LOOKUP
 template <int VEC, bool TMA, int NCH>
 __global__ void __launch_bounds__(kThreads, 1)
 lookup_kernel(const __grid_constant__ RowParams rp, int V, const int32_t* __restrict__ syms,
               uint32_t* __restrict__ pairs, uint32_t* __restrict__ status) {
-    __shared__ Ctl ctl;
-    RowEngine<VEC, TMA, NCH> eng;
-    eng.setup(V, &ctl, g_ring);
-    const int warp = eng.warp, lane = eng.lane, gbeg = eng.gbeg, gend = eng.gend;
+    using Eng = RowEngine<VEC, TMA, NCH>;
+    Ctl& ctl = g_ctl;
+    Eng eng;
+    eng.setup();
     RowSeq seq;
     seq.init(rp);
-    if (seq.valid(rp)) eng.issue(seq.ptr(rp));
+    if (seq.valid(rp)) Eng::issue(seq.ptr(rp), V);
     while (seq.valid(rp)) {
         const int64_t r = seq.s;
         const float* row = seq.ptr(rp);
         const int sym = __ldg(syms + r);  // issued now, consumed after the row's compute phases
         seq.next(rp);
         uint32_t q[kPerThread];
-        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, q);
+        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, V, q);
+        const int warp = Eng::warp(), lane = Eng::lane(), gbeg = Eng::gbeg(V), gend = Eng::gend(V);
         if (sym < 0 || sym >= V) {
             if (threadIdx.x == 0) {
                 *reinterpret_cast<uint2*>(pairs + 2 * r) = make_uint2(0u, 0u);
@@ -423,7 +436,7 @@ lookup_kernel(const __grid_constant__ RowParams rp, int V, const int32_t* __rest
             qs = warp_sum48(qs);
             eng.wait_done();
             if (lane == 0) {
-                const lq::Scale sc = eng.scale();
+                const lq::Scale sc = Eng::scale();
                 const uint64_t C = ctl.pref[warp] + part;
                 uint2 o;
                 o.x = lq::cum_of(C, (uint32_t)sym, sc);
@@ -439,22 +452,23 @@ lookup_kernel(const __grid_constant__ RowParams rp, int V, const int32_t* __rest
 template <int VEC, bool TMA, int NCH>
 __global__ void __launch_bounds__(kThreads, 1)
 build_kernel(const __grid_constant__ RowParams rp, int V, uint32_t* __restrict__ cum) {
-    __shared__ Ctl ctl;
-    RowEngine<VEC, TMA, NCH> eng;
-    eng.setup(V, &ctl, g_ring);
-    const int warp = eng.warp, lane = eng.lane, gbeg = eng.gbeg, gend = eng.gend;
+    using Eng = RowEngine<VEC, TMA, NCH>;
+    Ctl& ctl = g_ctl;
+    Eng eng;
+    eng.setup();
     RowSeq seq;
     seq.init(rp);
-    if (seq.valid(rp)) eng.issue(seq.ptr(rp));
+    if (seq.valid(rp)) Eng::issue(seq.ptr(rp), V);
     while (seq.valid(rp)) {
         const int64_t r = seq.s;
         const float* row = seq.ptr(rp);
         seq.next(rp);
         uint32_t q[kPerThread];
-        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, q);
+        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, V, q);
+        const int warp = Eng::warp(), lane = Eng::lane(), gbeg = Eng::gbeg(V), gend = Eng::gend(V);
         eng.wait_done();
         uint64_t base = ctl.pref[warp];
-        const lq::Scale sc = eng.scale();
+        const lq::Scale sc = Eng::scale();
         uint32_t* out = cum + r * (int64_t)V;
         constexpr int IT = kPerThread / VEC;
 #pragma unroll
@@ -518,14 +532,14 @@ __global__ void __launch_bounds__(kThreads, 1)
 decode_kernel(const __grid_constant__ RowParams rp, int V, lac_dec_state* __restrict__ state,
               const uint8_t* __restrict__ bytes, const int64_t* __restrict__ offsets,
               int32_t* __restrict__ syms, int64_t sym_stride, int P) {
-    __shared__ Ctl ctl;
-    RowEngine<VEC, TMA, NCH> eng;
-    eng.setup(V, &ctl, g_ring);
-    const int warp = eng.warp, lane = eng.lane, gbeg = eng.gbeg, gend = eng.gend;
+    using Eng = RowEngine<VEC, TMA, NCH>;
+    Ctl& ctl = g_ctl;
+    Eng eng;
+    eng.setup();
     constexpr int IT = kPerThread / VEC;
     RowSeq seq;
     seq.init(rp);
-    if (seq.valid(rp)) eng.issue(seq.ptr(rp));
+    if (seq.valid(rp)) Eng::issue(seq.ptr(rp), V);
     uint32_t par = 0;  // which DecShared buffer the current stream uses
     while (seq.valid(rp)) {
         const int64_t s = seq.s;
@@ -541,12 +555,13 @@ decode_kernel(const __grid_constant__ RowParams rp, int V, lac_dec_state* __rest
         }
         uint32_t q[kPerThread];
         DecShared& dec = ctl.dec[par];
-        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, q, &dec);
+        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, V, q, &dec);
         eng.wait_done();
+        const int warp = Eng::warp(), lane = Eng::lane(), gbeg = Eng::gbeg(V), gend = Eng::gend(V);
         if (warp == ctl.owner) {
             const uint64_t w = (uint64_t)(dec.high - dec.low + 1);
             const uint64_t xr = (uint64_t)(dec.value - dec.low);
-            const lq::Scale sc = eng.scale();
+            const lq::Scale sc = Eng::scale();
             const uint64_t Cb = ctl.pref[warp];
             // ---- owner warp: IT interleaved lane scans of the group sums, then one ballot per slab.
             // Groups are ordered (slab k, lane); cum is monotone in that order, so the number of groups

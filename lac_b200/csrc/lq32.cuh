@@ -5,15 +5,19 @@
 // result does not depend on how a row is split across threads, warps or CTAs:
 //
 //   m    = max_i x_i                               (NaN dropped)
-//   d_i  = x_i - m
-//   t_i  = fma(d_i, log2e, 1.5 * 2^23)             low mantissa bits = n_i = rne(d_i * log2e)
-//   f_i  = fma(d_i, log2e, 1.5 * 2^23 - t_i)       in [-0.5, 0.5], single rounding
-//   z_i  = fma(fma(fma(c3, f, c2), f, c1), f, 1.5 * 2^23)               c_k = minimax 2^f coefficients * 2^22
-//   P_i  = bits(z_i) & 0x7FFFFF = rne(2^22 * 2^f_i)  (max rel. error 1.02e-4, i.e. < 1e-8 bits/token; no F2I: the XU pipe that
-//          executes float->int conversions runs at ~4 threads/clk/SM on B200 and was the measured limiter)
-//   q_i  = n_i < -31 (or NaN / -inf) ? 0 : (P_i << 9) >> -n_i    (integer, <= 2^31)
+//   nref = bits(fma(m, log2e, 1.5 * 2^23))         t = fma(x, log2e, 1.5*2^23) is monotone in x, so nref = max_i bits(t_i);
+//                                                  the low mantissa bits of t are rne(x * log2e).  No "x - m" is ever formed.
+//                                                  Row is DEGENERATE (all q = 0) if nref is outside [kRefLo, kRefHi):
+//                                                  +inf, |m log2e| >= 2^22 - 64, or nothing finite.
+//   t_i  = fma(x_i, log2e, 1.5 * 2^23),  sh_i = nref - bits(t_i)      (unsigned; >= 32 for -inf and NaN)
+//   f_i  = fma(x_i, log2e, 1.5 * 2^23 - t_i)       in [-0.5, 0.5], single rounding
+//   z_i  = fma(fma(fma(c3, f, c2), f, c1), f, 1.5 * 2^25)     c_k = minimax 2^f coefficients * 2^24; z in [2^25, 2^26)
+//   q_i  = sh_i >= 32 ? 0 : (bits(z_i) << 7) >> sh_i   mantissa(z) = rne(2^22 2^f) (max rel. error 1.02e-4); the
+//                                                  exponent field of that binade ends in 00, so bits(z) << 7 is the
+//                                                  clean integer mantissa << 7 < 2^29.5 and four q fit a uint32 sum.
+//          No F2I anywhere: float->int conversion runs at 16 threads/clk/SM on B200 (measured limiter).
 //   Q    = sum_i q_i,  C_i = sum_{j<i} q_j          (exact, order independent)
-//   s    = bitlen(Q) - 1,  R = floor(((2^32 - V) << 31) / ((Q >> (s - 31)) + 1))
+//   s    = bitlen(Q) - 1,  Qn = Q normalised to [2^31, 2^32),  R = floor(((2^32 - V) << 31) / (Qn + 1))
 //   cum_i = ((C_i * R) >> s) + i,  cum_V = 2^32     => every frequency >= 1
 //
 // Replaces the reference's float table builders (llama_compress.py:24-30,
@@ -26,24 +30,28 @@
 namespace lq {
 
 __device__ __forceinline__ float log2e() { return __uint_as_float(0x3FB8AA3Bu); }
-__device__ __forceinline__ float magic() { return __uint_as_float(0x4B400000u); }  // 1.5 * 2^23
-constexpr uint32_t kC1 = 0x4a317afdu, kC2 = 0x49780626u, kC3 = 0x4861510cu;  // minimax 2^f, degree 3, * 2^22
+__device__ __forceinline__ float magic() { return __uint_as_float(0x4B400000u); }   // 1.5 * 2^23
+__device__ __forceinline__ float magicz() { return __uint_as_float(0x4C400000u); }  // 1.5 * 2^25
+constexpr uint32_t kC1 = 0x4b317afdu, kC2 = 0x4a780626u, kC3 = 0x4961510cu;  // minimax 2^f, degree 3, * 2^24
 
 __device__ __forceinline__ float neg_inf() { return __uint_as_float(0xFF800000u); }
 
-// fmaxf drops a NaN operand, like PTX max.f32 and the oracle's lq_max.
-__device__ __forceinline__ float vmax(float a, float b) { return fmaxf(a, b); }
+constexpr int kRefLo = 0x4B000040, kRefHi = 0x4B800000;
 
-__device__ __forceinline__ uint32_t q_of(float x, float m) {
-    float d = __fsub_rn(x, m);
-    float t = __fmaf_rn(d, log2e(), magic());
-    uint32_t sh = 0x4B400000u - __float_as_uint(t);  // -n for n in [-31, 0]; >= 32 otherwise
-    float f = __fmaf_rn(d, log2e(), __fsub_rn(magic(), t));
+__device__ __forceinline__ bool ref_valid(int nref) { return nref >= kRefLo && nref < kRefHi; }
+// reference exponent of a row (or of any part of it) from its float maximum
+__device__ __forceinline__ int ref_of_max(float m) { return __float_as_int(__fmaf_rn(m, log2e(), magic())); }
+
+// scalar form of the per-element step (the kernels use the packed two-lane version)
+__device__ __forceinline__ uint32_t q_of(float x, int nref) {
+    float t = __fmaf_rn(x, log2e(), magic());
+    uint32_t sh = (uint32_t)nref - __float_as_uint(t);
+    float f = __fmaf_rn(x, log2e(), __fsub_rn(magic(), t));
     float p = __uint_as_float(kC3);
     p = __fmaf_rn(p, f, __uint_as_float(kC2));
     p = __fmaf_rn(p, f, __uint_as_float(kC1));
-    float z = __fmaf_rn(p, f, magic());
-    return __funnelshift_rc(__float_as_uint(z) << 9, 0u, sh);  // (P << 9) >> min(sh, 32)
+    float z = __fmaf_rn(p, f, magicz());
+    return __funnelshift_rc(__float_as_uint(z) << 7, 0u, sh);  // (mantissa << 7) >> min(sh, 32)
 }
 
 struct Scale {
@@ -57,10 +65,10 @@ __device__ __forceinline__ Scale make_scale(uint64_t Q, int V) {
     k.Q = Q;
     k.R = 0;
     k.s = 0;
-    if (Q >= (1ull << 31)) {  // else: the degenerate Q == 0 row (no finite maximum)
-        k.s = 63 - __clzll((long long)Q);  // >= 31: the row maximum contributes q = 2^31
+    if (Q >= (1ull << 28)) {  // else: the degenerate Q == 0 row
+        k.s = 63 - __clzll((long long)Q);  // >= 28: the row maximum contributes q >= 2^28.5
         const uint64_t N = ((1ull << 32) - (uint64_t)V) << 31;
-        const uint64_t D = (Q >> (k.s - 31)) + 1;  // (2^31, 2^32]
+        const uint64_t D = (k.s >= 31 ? (Q >> (k.s - 31)) : (Q << (31 - k.s))) + 1;  // (2^31, 2^32]
         // R = floor(N / D) <= M * 2^s / Q.  fp64 estimate (off by at most 1) + exact fix-up:
         // far shorter dependent chain than the generic 64-bit division.
         uint64_t r = (uint64_t)__ddiv_rz((double)N, (double)D);

@@ -443,57 +443,66 @@ int orc_acs_decode(int prec, const uint64_t *cdf, int64_t stride, int64_t ntab, 
 /* ================================================================== */
 #define LQ_LOG2E 0x3FB8AA3Bu
 #define LQ_MAGIC 0x4B400000u /* 1.5 * 2^23 */
-/* minimax 2^f on [-0.5, 0.5], degree 3, scaled by 2^22: c1..c3 (max rel. error 1.02e-4); the constant
- * term 2^22 is folded into MAGIC */
-static const uint32_t LQ_C[4] = {0x4a800000u, 0x4a317afdu, 0x49780626u, 0x4861510cu};
+/* minimax 2^f on [-0.5, 0.5], degree 3, scaled by 2^24: c1..c3 (max rel. error 1.02e-4); the constant
+ * term is folded into LQ_MAGICZ = 1.5 * 2^25, so z lands in [2^25, 2^26) where one ulp is 4 */
+#define LQ_MAGICZ 0x4C400000u
+static const uint32_t LQ_C[4] = {0x4b800000u, 0x4b317afdu, 0x4a780626u, 0x4961510cu};
 static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
-/* fmaxf semantics of PTX max.f32: NaN operand is dropped. */
-static inline float lq_max(float a, float b) {
+/* LQ32 steps 1-4.  No subtraction of the maximum, no float->int conversion:
+ * integers are read out of float mantissas.
+ *   m    = max_i x_i  (NaN dropped)
+ *   nref = bits(fma(m, log2e, MAGIC))   MAGIC = 1.5 * 2^23; t = fma(x, log2e, MAGIC) is monotone in x, so this is
+ *                                  max_i bits(t_i); for |x*log2e| < 2^22 the low mantissa bits of t hold rne(x*log2e).
+ *                                  The row is DEGENERATE (all q = 0, uniform table) when nref is outside
+ *                                  [LQ_REF_LO, LQ_REF_HI): +inf, |m*log2e| >= 2^22 - 64, or nothing finite.
+ *   t_i  = fma(x_i, log2e, MAGIC),  sh_i = nref - bits(t_i)   (unsigned; = n_max - n_i; >= 32 for -inf; NaN -> q = 0)
+ *   f_i  = fma(x_i, log2e, MAGIC - t_i)     residual in [-0.5, 0.5], single rounding
+ *   z_i  = fma(fma(fma(c3, f, c2), f, c1), f, MAGICZ)   = 1.5*2^25 + 2^24 (2^f - 1); mantissa = rne(2^22 2^f)
+ *   q_i  = sh_i >= 32 ? 0 : (bits(z_i) << 7) >> sh_i    (bits(z) << 7 = mantissa << 7 in [2^28.5, 2^29.5): the
+ *                                  exponent field of [2^25, 2^26) ends in 00, so four q fit a uint32 sum)
+ */
+#define LQ_REF_LO 0x4B000040
+#define LQ_REF_HI 0x4B800000
+#define LQ_DEGENERATE INT32_MIN
+static inline float lq_max(float a, float b) { /* PTX max.f32 / fmaxf: a NaN operand is dropped */
     if (a != a) return b;
     if (b != b) return a;
     return a > b ? a : b;
 }
-/* q_i ~ 2^((x_i - m) * log2 e) * 2^31 per DESIGN.md section 3 steps 2-4 (no float->int conversion
- * instruction anywhere: integers are read out of float mantissas):
- *   d = x - m                      (<= 0, or NaN / -inf)
- *   t = fma(d, log2e, MAGIC)       MAGIC = 1.5 * 2^23: the low mantissa bits of t hold n = rne(d*log2e)
- *   sh = MAGIC_BITS - bits(t)      (unsigned; = -n for n in [-31, 0], >= 32 for everything else incl. NaN)
- *   f = fma(d, log2e, MAGIC - t)   residual in [-0.5, 0.5], single rounding
- *   z = fma(fma(fma(c3, f, c2), f, c1), f, MAGIC)                = 1.5*2^23 + 2^22 (2^f - 1), ulp 1
- *   P = bits(z) & 0x7FFFFF         = rne(2^22 * 2^f) in [2^21.5, 2^22.5]
- *   q = sh >= 32 ? 0 : (P << 9) >> sh */
-static inline uint32_t lq_q(float x, float m) {
-    float d = x - m;
-    float t = fmaf(d, u2f(LQ_LOG2E), u2f(LQ_MAGIC));
-    uint32_t sh = LQ_MAGIC - f2u(t);
+static inline int32_t lq_rowref(const float *x, int V) {
+    float m = u2f(0xFF800000u); /* -inf */
+    for (int i = 0; i < V; i++) m = lq_max(m, x[i]);
+    int32_t nref = (int32_t)f2u(fmaf(m, u2f(LQ_LOG2E), u2f(LQ_MAGIC)));
+    if (nref < LQ_REF_LO || nref >= LQ_REF_HI) return LQ_DEGENERATE;
+    return nref;
+}
+static inline uint32_t lq_q(float x, int32_t nref) {
+    if (nref == LQ_DEGENERATE || x != x) return 0u;
+    float t = fmaf(x, u2f(LQ_LOG2E), u2f(LQ_MAGIC));
+    uint32_t sh = (uint32_t)nref - f2u(t);
     if (sh >= 32) return 0u;
     float rn = u2f(LQ_MAGIC) - t;
-    float f = fmaf(d, u2f(LQ_LOG2E), rn);
+    float f = fmaf(x, u2f(LQ_LOG2E), rn);
     float p = u2f(LQ_C[3]);
     p = fmaf(p, f, u2f(LQ_C[2]));
     p = fmaf(p, f, u2f(LQ_C[1]));
-    float z = fmaf(p, f, u2f(LQ_MAGIC));
-    return (f2u(z) << 9) >> sh;
-}
-static inline float lq_rowmax(const float *x, int V) {
-    float m = u2f(0xFF800000u); /* -inf */
-    for (int i = 0; i < V; i++) m = lq_max(m, x[i]);
-    return m;
+    float z = fmaf(p, f, u2f(LQ_MAGICZ));
+    return (f2u(z) << 7) >> sh;
 }
 typedef struct { uint64_t Q; uint32_t R; int s; } lq_scale;
 static inline lq_scale lq_make_scale(uint64_t Q, int V) {
-    /* s = bitlen(Q) - 1 (>= 31 whenever Q != 0: the row maximum contributes q = 2^31);
-     * D = (Q >> (s - 31)) + 1 in (2^31, 2^32];  R = floor((M << 31) / D) <= M * 2^s / Q,
-     * so sum_i floor(q_i-prefix scaling) never exceeds M = 2^32 - V. */
+    /* s = bitlen(Q) - 1 (>= 28 whenever Q != 0: the row maximum contributes q >= 2^28.5);
+     * Qn = Q normalised to [2^31, 2^32);  D = Qn + 1;  R = floor((M << 31) / D) <= M * 2^s / Q,
+     * so the scaled prefix sums never exceed M = 2^32 - V. */
     lq_scale k = {Q, 0, 0};
-    if (Q < ((uint64_t)1 << 31)) return k; /* only the degenerate Q == 0 row (no finite maximum) */
+    if (Q < ((uint64_t)1 << 28)) return k; /* only the degenerate Q == 0 row */
     int b = 64 - __builtin_clzll(Q);
     k.s = b - 1;
     uint64_t M = ((uint64_t)1 << 32) - (uint64_t)V;
-    uint64_t D = (Q >> (k.s - 31)) + 1;
-    k.R = (uint32_t)((M << 31) / D);
+    uint64_t Qn = k.s >= 31 ? (Q >> (k.s - 31)) : (Q << (31 - k.s));
+    k.R = (uint32_t)((M << 31) / (Qn + 1));
     return k;
 }
 static inline uint32_t lq_cum(uint64_t C, uint32_t i, lq_scale k) {
@@ -504,7 +513,7 @@ int orc_lq32_cdf(const float *logits, int64_t rows, int V, int64_t row_stride, u
     if (V < 1 || V > (1 << 20)) return ORC_E_ARG;
     for (int64_t r = 0; r < rows; r++) {
         const float *x = logits + r * row_stride;
-        float m = lq_rowmax(x, V);
+        int32_t m = lq_rowref(x, V);
         uint64_t Q = 0;
         for (int i = 0; i < V; i++) Q += lq_q(x[i], m);
         lq_scale k = lq_make_scale(Q, V);
@@ -523,7 +532,7 @@ int orc_lq32_lookup(const float *logits, int64_t rows, int V, int64_t row_stride
         const float *x = logits + r * row_stride;
         int32_t s = syms[r];
         if (s < 0 || s >= V) return ORC_E_SYMBOL;
-        float m = lq_rowmax(x, V);
+        int32_t m = lq_rowref(x, V);
         uint64_t Q = 0, C = 0, qs = 0;
         for (int i = 0; i < V; i++) {
             uint32_t q = lq_q(x[i], m);

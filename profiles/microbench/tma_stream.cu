@@ -48,6 +48,36 @@ __global__ void __launch_bounds__(1024, 1) stream(const unsigned char* src, size
     if (acc == 12345.f) sink[0] = acc;
 }
 
+// mode "row": emulate the product kernels' row loop.  Per row of `slots` chunks: wait for every chunk, read it
+// to registers (LDS.128), barrier, re-arm all chunks with the next row, then spin `spin` clocks (the compute phase).
+__global__ void __launch_bounds__(1024, 1) rowloop(const unsigned char* src, size_t total, int slots, int slot_bytes, int spin, float* sink) {
+    __shared__ uint64_t bar[32];
+    size_t row_bytes = (size_t)slots * slot_bytes;
+    size_t per_cta = total / gridDim.x / row_bytes * row_bytes;
+    const unsigned char* base = src + (size_t)blockIdx.x * per_cta;
+    int nrows = (int)(per_cta / row_bytes);
+    if (threadIdx.x == 0) { for (int i = 0; i < slots; i++) mbar_init(&bar[i], 1); asm volatile("fence.mbarrier_init.release.cluster;"); }
+    __syncthreads();
+    if (threadIdx.x == 0) for (int i = 0; i < slots; i++) { mbar_expect_tx(&bar[i], slot_bytes); tma(ring + (size_t)i * slot_bytes, base + (size_t)i * slot_bytes, slot_bytes, &bar[i]); }
+    float acc = 0;
+    for (int r = 0; r < nrows; r++) {
+        for (int s = 0; s < slots; s++) {
+            mbar_wait(&bar[s], r & 1);
+            const float4* p = reinterpret_cast<const float4*>(ring + (size_t)s * slot_bytes);
+            for (int i = threadIdx.x; i < slot_bytes / 16; i += 1024) { float4 v = p[i]; acc += v.x + v.y + v.z + v.w; }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && r + 1 < nrows) {
+            asm volatile("fence.proxy.async.shared::cta;");
+            for (int s = 0; s < slots; s++) { mbar_expect_tx(&bar[s], slot_bytes); tma(ring + (size_t)s * slot_bytes, base + (size_t)(r + 1) * row_bytes + (size_t)s * slot_bytes, slot_bytes, &bar[s]); }
+        }
+        long long t0 = clock64();
+        while (clock64() - t0 < spin) {}
+        __syncthreads();
+    }
+    if (acc == 12345.f) sink[0] = acc;
+}
+
 __global__ void ldg_read(const float4* src, size_t n, float* sink) {
     float acc = 0;
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
@@ -61,14 +91,16 @@ __global__ void ldg_read(const float4* src, size_t n, float* sink) {
     if (acc == 12345.f) sink[0] = acc;
 }
 
-int main() {
+int main(int argc, char** argv) {
+    const bool only_rowloop = argc > 1;
     size_t total = (size_t)2 << 30;
     unsigned char* src; float* sink;
     cudaMalloc(&src, total); cudaMalloc(&sink, 4); cudaMemset(src, 1, total);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaFuncSetAttribute(stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(rowloop, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     int cfgs[][2] = {{4, 16384}, {8, 16384}, {12, 16384}, {13, 16384}, {4, 32768}, {6, 32768}, {2, 65536}, {3, 65536}, {16, 8192}, {24, 8192}};
-    for (int mode = 0; mode < 2; mode++)
+    for (int mode = 0; mode < 2 && !only_rowloop; mode++)
         for (auto& c : cfgs) {
             size_t smem = (size_t)c[0] * c[1];
             float best = 1e9;
@@ -79,6 +111,19 @@ int main() {
                 float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
             }
             printf("mode %d slots %2d x %5d B (%3zu KB in flight/SM): %.3f ms  %.0f GB/s  %s\n", mode, c[0], c[1], smem / 1024, best, total / best / 1e6, cudaGetErrorString(cudaGetLastError()));
+        }
+    for (int slots : {2, 4})
+        for (int spin : {0, 1000, 2000, 3000, 4000, 5000, 6000}) {
+            int sb = 131072 / slots;
+            float best = 1e9;
+            for (int rep = 0; rep < 3; rep++) {
+                cudaEventRecord(e0);
+                rowloop<<<148, 1024, 131072>>>(src, total, slots, sb, spin, sink);
+                cudaEventRecord(e1); cudaEventSynchronize(e1);
+                float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+            }
+            double rows = (double)(total / 148 / 131072);
+            printf("rowloop %d x %6d B, spin %4d clk: %.3f ms  %.0f GB/s  %.2f us/row  %s\n", slots, sb, spin, best, total / best / 1e6, best * 1e3 / rows, cudaGetErrorString(cudaGetLastError()));
         }
     for (int blocks : {148 * 2, 148 * 4, 148 * 8, 148 * 16}) {
         float best = 1e9;
