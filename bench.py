@@ -41,8 +41,8 @@ UNIT = "tokens/s"
 
 def workload_config(n_gpus):
     return {
-        "workload": "coder-only sweep: precomputed random fp32 logits, vocab 32000, 1024 streams x 2048 tokens, "
-                    "encode+decode",
+        "workload": f"coder-only sweep: precomputed random fp32 logits, vocab {VOCAB}, {STREAMS} streams x "
+                    f"{CHUNK_TOKENS} tokens, encode+decode",
         "vocab": VOCAB,
         "streams_per_gpu": STREAMS,
         "tokens_per_stream": CHUNK_TOKENS,
@@ -297,7 +297,7 @@ def run_gpu(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32->u32/u64", "data": "synthetic", "config": workload_config(world),
-            "roofline": {"bound": "hbm", "kernel": "lookup_kernel<4> (fused softmax->quantise->clamp->prefix-sum CDF lookup)",
+            "roofline": {"bound": "hbm", "kernel": "lookup_kernel (fused softmax -> fixed-total quantisation -> clamp -> prefix sums -> (lo, hi) of the coded symbol)",
                          "achieved": look_gbs, "peak": peak, "unit": "GB/s", "frac": look_gbs / peak,
                          "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "ms_per_launch": lookup_ms,
@@ -322,7 +322,12 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    # measurement switches (the driver's contract run uses the defaults = BASELINE.json configs[1])
+    ap.add_argument("--vocab", type=int, default=VOCAB)
+    ap.add_argument("--streams", type=int, default=STREAMS)
+    ap.add_argument("--slice", type=int, default=SLICE)
     args = ap.parse_args()
+    globals().update(VOCAB=args.vocab, STREAMS=args.streams, SLICE=args.slice)
     if args.impl == "reference":
         run_reference(args)
     else:

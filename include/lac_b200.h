@@ -56,7 +56,8 @@ int lac_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *hbm_by
  * frequency >= 1, bit-exact with oracle/lac_oracle.c:orc_lq32_cdf.
  *
  * d_logits  [rows] rows of `vocab` fp32, row r at d_logits + r * row_stride (elements)
- * vocab     1 .. 1048576
+ * vocab     1 .. 262144; above 32768 the row is split over a thread-block cluster and must be 16-byte
+ *           aligned (vocab and strides multiples of 4, base 16-byte aligned)
  * ---------------------------------------------------------------------------------- */
 
 /* Full table: d_cum[r * vocab + i] = exclusive cumulative frequency of symbol i (cum[0] = 0;

@@ -17,6 +17,7 @@ cudaError_t launch_decode(const float*, int64_t, int64_t, int64_t, int64_t, int,
                           const uint8_t*, const int64_t*, int32_t*, int64_t, int, cudaStream_t);
 cudaError_t launch_dec_init(lac_dec_state*, int64_t, int, const uint8_t*, const int64_t*, cudaStream_t);
 int max_vocab_single_cta();
+int max_vocab();
 cudaError_t launch_enc_init(lac_enc_state*, int64_t, int, cudaStream_t);
 cudaError_t launch_encode_pairs(const uint32_t*, int64_t, int64_t, int64_t, int64_t, const int32_t*, lac_enc_state*,
                                 uint8_t*, int64_t, int, int, cudaStream_t);
@@ -57,11 +58,15 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 bool prec_ok(int prec, int lo) { return prec >= lo && prec <= 60; }
 
-int check_vocab(int32_t vocab) {
-    if (vocab < 1 || vocab > (1 << 20)) return fail(LAC_E_ARG, "vocab %d out of range [1, 2^20]", vocab);
-    if (vocab > lac::max_vocab_single_cta())
-        return fail(LAC_E_ARG, "vocab %d > %d needs the cluster kernel (not built in this revision)", vocab,
-                    lac::max_vocab_single_cta());
+int check_vocab(int32_t vocab, const void* logits = nullptr, int64_t s0 = 0, int64_t s1 = 0) {
+    if (vocab < 1 || vocab > lac::max_vocab())
+        return fail(LAC_E_ARG, "vocab %d out of range [1, %d]", vocab, lac::max_vocab());
+    if (vocab > lac::max_vocab_single_cta()) {
+        // rows wider than one CTA's registers are split over a thread-block cluster, TMA-staged only
+        if (vocab % 4 != 0 || (((uintptr_t)logits) & 15) != 0 || s0 % 4 != 0 || s1 % 4 != 0)
+            return fail(LAC_E_ARG, "vocab %d > %d needs 16-byte aligned rows (vocab and strides multiples of 4)", vocab,
+                        lac::max_vocab_single_cta());
+    }
     return LAC_OK;
 }
 
@@ -87,7 +92,7 @@ int lac_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_by
 int lac_cdf_build_f32(const float* d_logits, int64_t rows, int32_t vocab, int64_t row_stride, uint32_t* d_cum,
                       void* stream) {
     if (!d_logits || !d_cum || rows < 0 || row_stride < vocab) return fail(LAC_E_ARG, "lac_cdf_build_f32: bad argument");
-    if (int rc = check_vocab(vocab)) return rc;
+    if (int rc = check_vocab(vocab, d_logits, row_stride)) return rc;
     CK(lac::launch_build(d_logits, rows, vocab, row_stride, d_cum, (cudaStream_t)stream), "lac_cdf_build_f32");
     return LAC_OK;
 }
@@ -96,7 +101,7 @@ int lac_cdf_lookup_f32(const float* d_logits, int64_t rows, int32_t vocab, int64
                        uint32_t* d_pairs, uint32_t* d_status, void* stream) {
     if (!d_logits || !d_syms || !d_pairs || rows < 0 || row_stride < vocab)
         return fail(LAC_E_ARG, "lac_cdf_lookup_f32: bad argument");
-    if (int rc = check_vocab(vocab)) return rc;
+    if (int rc = check_vocab(vocab, d_logits, row_stride)) return rc;
     CK(lac::launch_lookup(d_logits, rows, vocab, row_stride, d_syms, d_pairs, d_status, (cudaStream_t)stream),
        "lac_cdf_lookup_f32");
     return LAC_OK;
@@ -136,7 +141,7 @@ int lac_ac_decode_logits_f32(const float* d_logits, int64_t n_streams, int64_t T
     if ((!d_logits && T > 0) || !d_state || !d_bytes || !d_offsets || (!d_syms && T > 0) || n_streams < 0 || T < 0)
         return fail(LAC_E_ARG, "lac_ac_decode_logits_f32: bad argument");
     if (!prec_ok(prec, 34)) return fail(LAC_E_ARG, "lac_ac_decode_logits_f32: prec %d outside [34, 60]", prec);
-    if (int rc = check_vocab(vocab)) return rc;
+    if (int rc = check_vocab(vocab, d_logits, stream_stride, tok_stride)) return rc;
     CK(lac::launch_decode(d_logits, n_streams, T, stream_stride, tok_stride, vocab, d_ntok, d_state, d_bytes,
                           d_offsets, d_syms, sym_stride, prec, (cudaStream_t)stream),
        "lac_ac_decode_logits_f32");

@@ -161,7 +161,56 @@ __device__ __forceinline__ uint64_t warp_incl_scan(uint64_t v, int lane) {
     return v;
 }
 
+// ------------------------------------------------------------------ thread-block cluster helpers
+// A row wider than one CTA can hold (32768 elements) is split over a cluster of CL CTAs; the two
+// row-level reductions travel through distributed shared memory with cluster-scope mbarriers.
+__device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_u64(uint32_t addr, uint64_t v) {
+    asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_cluster_u64(uint32_t addr) {
+    uint64_t v;
+    asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t remote_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITC_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONEC_%=;\n\t"
+        "bra WAITC_%=;\n\t"
+        "DONEC_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int CL>
+struct Clu {
+    static __device__ __forceinline__ uint32_t rank() {
+        if (CL == 1) return 0;
+        uint32_t r;
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+        return r;
+    }
+    static __device__ __forceinline__ uint32_t id() { return CL == 1 ? blockIdx.x : blockIdx.x / CL; }
+    static __device__ __forceinline__ uint32_t count() { return CL == 1 ? gridDim.x : gridDim.x / CL; }
+};
+
 // ------------------------------------------------------------------ shared control block
+constexpr int kMaxCluster = 8;
 struct DecShared {
     int64_t low, high, value;
     uint64_t pos;             // next bit of the stream
@@ -169,24 +218,28 @@ struct DecShared {
     uint64_t win_byte;
     int64_t data_off;
     uint64_t nbytes;
-    uint32_t status;
 };
+constexpr int kDecWords = sizeof(DecShared) / 8;
 
 struct Ctl {
     uint64_t full[kMaxChunks];  // TMA chunk landed
     uint64_t done;              // row-level bookkeeping published (phase = row parity)
+    uint64_t cl_max_bar;        // cluster: every CTA's maximum has arrived (count CL)
+    uint64_t cl_sum_bar;        // cluster: every CTA's total has arrived (count CL)
+    uint64_t cl_Q[2][kMaxCluster];  // per-CTA totals, double-buffered by row parity
+    int cl_max[2][kMaxCluster];     // per-CTA maxima (ordered ints)
     int red_max[2][kWarps];     // per-warp maxima (order-preserving ints), double-buffered by row parity
     uint64_t wsum[kWarps];      // per-warp totals of q
-    uint64_t pref[kWarps];      // exclusive prefix of wsum   } written once per row by the last warp
-    uint64_t Q;                 // sum of wsum                } to finish phase B, then `done` flips
-    uint32_t R;                 // lq::Scale                  }
-    int s;                      //                            }
-    int owner;                  // decode: warp whose segment holds the symbol
+    uint64_t pref[kWarps];      // row-wide exclusive prefix at each warp } written once per row by the last
+    uint64_t Q;                 // row total                               } warp to finish phase B, then
+    uint32_t R;                 // lq::Scale                               } `done` flips
+    int s;                      //                                         }
+    int owner;                  // decode: local warp whose segment holds the symbol, or -1
     uint32_t arrive;            // warps done with phase B of the current row
-    DecShared dec[2];
+    DecShared dec[2];           // decoder state (rank 0's copy is the live one), double-buffered by row parity
 };
 
-// Rows visited by this CTA, in order: outer index s = blockIdx.x, += gridDim.x; inner t < Ts.
+// Rows visited by this CTA / cluster, in order: outer index s = first, += stride; inner t < Ts.
 // RowParams stays in the kernel-parameter constant bank; only (s, t, Ts) live in registers.
 struct RowParams {
     const float* base;
@@ -196,54 +249,59 @@ struct RowParams {
 struct RowSeq {
     int64_t s;
     int t, Ts;
-    __device__ __forceinline__ void skip_empty(const RowParams& p) {
+    __device__ __forceinline__ void skip_empty(const RowParams& p, uint32_t stride) {
         while (s < p.n_outer) {
             Ts = p.ntok ? p.ntok[s] : (int)p.T;
             if (Ts > 0) break;
-            s += gridDim.x;
+            s += stride;
         }
     }
-    __device__ __forceinline__ void init(const RowParams& p) {
-        s = blockIdx.x;
+    __device__ __forceinline__ void init(const RowParams& p, uint32_t first, uint32_t stride) {
+        s = first;
         t = 0;
         Ts = 0;
-        skip_empty(p);
+        skip_empty(p, stride);
     }
     __device__ __forceinline__ bool valid(const RowParams& p) const { return s < p.n_outer; }
     __device__ __forceinline__ const float* ptr(const RowParams& p) const { return p.base + s * p.so + t * p.st; }
-    __device__ __forceinline__ void next(const RowParams& p) {
+    __device__ __forceinline__ void next(const RowParams& p, uint32_t stride) {
         if (++t >= Ts) {
-            s += gridDim.x;
+            s += stride;
             t = 0;
-            skip_empty(p);
+            skip_empty(p, stride);
         }
     }
 };
 
-// ------------------------------------------------------------------ row engine: staging + passes + finish
+// ------------------------------------------------------------------ row engine: staging + phases + finish
 // File-scope shared objects have compile-time addresses, and everything about the row geometry is
 // recomputed from (warp, V) on demand, so the engine keeps ONE register of state (the row counter):
 // with 32 row elements per thread and a 64-register budget nothing else may stay live in the hot loop.
 __shared__ Ctl g_ctl;
 extern __shared__ __align__(128) unsigned char g_ring[];
 
-template <int VEC, bool TMA, int NCH>
+template <int VEC, bool TMA, int NCH, int CL>
 struct RowEngine {
+    static_assert(CL == 1 || (TMA && VEC == 4), "cluster rows use the TMA path");
     static constexpr int IT = kPerThread / VEC;
     static constexpr int kWarpsPerChunk = Ring<NCH>::kWarpsPerChunk;
     static constexpr int kSlotBytes = Ring<NCH>::kSlotBytes;
+    static constexpr int kTotWarps = CL * kWarps;
     uint32_t it;
 
     static __device__ __forceinline__ int warp() { return threadIdx.x >> 5; }
     static __device__ __forceinline__ int lane() { return threadIdx.x & 31; }
+    static __device__ __forceinline__ int gwarp() { return (int)Clu<CL>::rank() * kWarps + warp(); }
     static __device__ __forceinline__ int groups(int V) { return V / VEC; }
-    static __device__ __forceinline__ int seg_begin(int w, int V) { return (int)(((int64_t)w * groups(V)) / kWarps); }
-    static __device__ __forceinline__ int gbeg(int V) { return seg_begin(warp(), V); }
-    static __device__ __forceinline__ int gend(int V) { return seg_begin(warp() + 1, V); }
+    // first float4 group of (row-wide) warp gw: the row is cut evenly over the CL * 32 warps of the cluster
+    static __device__ __forceinline__ int seg_begin(int gw, int V) { return (int)(((int64_t)gw * groups(V)) / kTotWarps); }
+    static __device__ __forceinline__ int gbeg(int V) { return seg_begin(gwarp(), V); }
+    static __device__ __forceinline__ int gend(int V) { return seg_begin(gwarp() + 1, V); }
     static __device__ __forceinline__ int chunk() { return warp() / kWarpsPerChunk; }
-    static __device__ __forceinline__ int cg0(int V) { return seg_begin(chunk() * kWarpsPerChunk, V); }
+    static __device__ __forceinline__ int chunk_gw0() { return (int)Clu<CL>::rank() * kWarps + chunk() * kWarpsPerChunk; }
+    static __device__ __forceinline__ int cg0(int V) { return seg_begin(chunk_gw0(), V); }
     static __device__ __forceinline__ uint32_t cbytes(int V) {
-        return (uint32_t)(seg_begin((chunk() + 1) * kWarpsPerChunk, V) - cg0(V)) * 16u;
+        return (uint32_t)(seg_begin(chunk_gw0() + kWarpsPerChunk, V) - cg0(V)) * 16u;
     }
     static __device__ __forceinline__ bool leader() { return (threadIdx.x & (32 * kWarpsPerChunk - 1)) == 0; }
     static __device__ __forceinline__ unsigned char* slot() { return g_ring + chunk() * kSlotBytes; }
@@ -254,9 +312,15 @@ struct RowEngine {
             g_ctl.arrive = 0;
             for (int i = 0; i < NCH; i++) mbar_init(&g_ctl.full[i], 1);
             mbar_init(&g_ctl.done, 1);
+            mbar_init(&g_ctl.cl_max_bar, CL);
+            mbar_init(&g_ctl.cl_sum_bar, CL);
             fence_mbar_init();
         }
         __syncthreads();
+        if (CL > 1) cluster_sync_all();  // nobody may signal a peer whose barriers are not initialised yet
+    }
+    static __device__ void teardown() {
+        if (CL > 1) cluster_sync_all();  // nobody may exit while a peer can still write into its shared memory
     }
     static __device__ __forceinline__ void issue(const float* row, int V) {  // chunk leader: arm + bulk copy
         if (TMA && leader()) {
@@ -268,12 +332,12 @@ struct RowEngine {
         }
     }
 
-    // One row: stage it into registers, phase A (maximum), the row's single block barrier, phase B (q, sums).
-    // `next_row` (or nullptr) is prefetched as soon as this row has left shared memory.  On return q[] holds
-    // this thread's final q values; the row-level results (g_ctl.pref, Q, R, s, owner) are valid once
-    // wait_done() returns.
+    // One row: stage it into registers, phase A (maximum), the row's single block barrier (plus, in a cluster,
+    // the exchange of the CTA maxima), phase B (q, sums).  `next_row` (or nullptr) is prefetched as soon as this
+    // row has left shared memory.  On return q[] holds this thread's q values; the row-level results
+    // (g_ctl.pref, Q, R, s, owner) are valid once wait_done() returns.  dec_mode: also find the decode owner.
     __device__ __forceinline__ void reduce(const float* __restrict__ row, const float* next_row, int V,
-                                           uint32_t (&q)[kPerThread], const DecShared* dec = nullptr) {
+                                           uint32_t (&q)[kPerThread], bool dec_mode = false, bool lazy = false) {
         float x[kPerThread];
         {
             const int gb = gbeg(V), ge = gend(V), ln = lane();
@@ -321,20 +385,45 @@ struct RowEngine {
             }
         }
         const int mw = __reduce_max_sync(0xffffffffu, f2ord(m));
-        int* red = g_ctl.red_max[it & 1];
+        const uint32_t par = it & 1;
+        int* red = g_ctl.red_max[par];
         if (lane() == 0) red[warp()] = mw;
         __syncthreads();  // the only block-wide barrier of the row
-        const int nref = lq::ref_of_max(ord2f(__reduce_max_sync(0xffffffffu, red[lane()])));
-        // phase B: q against the row-wide reference, uint32 sums per 4 elements (4 q < 2^31.5), uint64 per lane
-        // (a degenerate row -- no finite maximum, +inf, out of range -- gets a reference that pushes every
-        // shift count past 31, i.e. q = 0 everywhere and the uniform table, without a second code path)
-        const uint32_t nref_u = lq::ref_valid(nref) ? (uint32_t)nref : 0xFFFFFFFFu;
+        int mx = __reduce_max_sync(0xffffffffu, red[lane()]);
+        if (CL > 1 && threadIdx.x < CL) {  // send this CTA's maximum to every CTA of the cluster (incl. itself)
+            st_cluster_u32(mapa(smem_u32(&g_ctl.cl_max[par][Clu<CL>::rank()]), threadIdx.x), (uint32_t)mx);
+            mbar_arrive_cluster(mapa(smem_u32(&g_ctl.cl_max_bar), threadIdx.x));
+        }
+        // phase B: q against the reference of THIS CTA's maximum, uint32 sums per 4 elements (4 q < 2^31.5).
+        // (a degenerate reference -- no finite maximum, +inf, out of range -- pushes every shift count past 31,
+        // i.e. q = 0 everywhere, without a second code path)
+        const int nloc = lq::ref_of_max(ord2f(mx));
+        const uint32_t nref_u = lq::ref_valid(nloc) ? (uint32_t)nloc : 0xFFFFFFFFu;
         uint64_t lane_sum = 0;
+        if (CL == 1) {
 #pragma unroll
-        for (int i = 0; i < kPerThread; i += 4) {
-            q_of2(x[i], x[i + 1], nref_u, q[i], q[i + 1]);
-            q_of2(x[i + 2], x[i + 3], nref_u, q[i + 2], q[i + 3]);
-            lane_sum += (q[i] + q[i + 1]) + (q[i + 2] + q[i + 3]);
+            for (int i = 0; i < kPerThread; i += 4) {
+                q_of2(x[i], x[i + 1], nref_u, q[i], q[i + 1]);
+                q_of2(x[i + 2], x[i + 3], nref_u, q[i + 2], q[i + 3]);
+                lane_sum += (q[i] + q[i + 1]) + (q[i + 2] + q[i + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < kPerThread; i += 2) q_of2(x[i], x[i + 1], nref_u, q[i], q[i + 1]);
+            // The other CTAs' maxima arrived while phase B ran.  q against the row-wide reference is the local
+            // q shifted by the distance of the two references: floor(floor(a / 2^j) / 2^k) = floor(a / 2^(j+k)).
+            mbar_wait_cluster(&g_ctl.cl_max_bar, par);
+#pragma unroll
+            for (int p = 0; p < CL; p++) mx = max(mx, g_ctl.cl_max[par][p]);
+            const int nref = lq::ref_of_max(ord2f(mx));
+            uint32_t delta = (uint32_t)nref - (uint32_t)nloc;
+            delta = (lq::ref_valid(nref) && delta < 32u) ? delta : 32u;
+#pragma unroll
+            for (int i = 0; i < kPerThread; i += 4) {
+#pragma unroll
+                for (int e = 0; e < 4; e++) q[i + e] = __funnelshift_rc(q[i + e], 0u, delta);
+                lane_sum += (q[i] + q[i + 1]) + (q[i + 2] + q[i + 3]);
+            }
         }
         const uint64_t ws = warp_sum48(lane_sum);
         uint32_t prev = 0;
@@ -344,18 +433,57 @@ struct RowEngine {
             prev = atomicAdd(&g_ctl.arrive, 1u);
         }
         prev = __shfl_sync(0xffffffffu, prev, 0);
-        if (prev == kWarps - 1) finish_row(V, dec);  // last warp of the row: every wsum[] is visible
+        if (prev == kWarps - 1) finish_row(V, par, dec_mode, lazy);  // last warp of the row: every wsum[] is visible
         it++;
     }
 
-    // Row-level bookkeeping, run by exactly one warp per row.
-    static __device__ __noinline__ void finish_row(int V, const DecShared* dec) {
+    // Decoder state lives in rank 0's shared memory (everyone reads / the owner lane writes it there).
+    static __device__ __forceinline__ uint64_t dec_ld(uint32_t buf, int word) {
+        const uint32_t a = smem_u32(reinterpret_cast<const uint64_t*>(&g_ctl.dec[buf]) + word);
+        if (CL == 1) return *(reinterpret_cast<const volatile uint64_t*>(&g_ctl.dec[buf]) + word);
+        return ld_cluster_u64(mapa(a, 0));
+    }
+    static __device__ __forceinline__ void dec_st(uint32_t buf, int word, uint64_t v) {
+        const uint32_t a = smem_u32(reinterpret_cast<const uint64_t*>(&g_ctl.dec[buf]) + word);
+        if (CL == 1) *(reinterpret_cast<volatile uint64_t*>(&g_ctl.dec[buf]) + word) = v;
+        else st_cluster_u64(mapa(a, 0), v);
+    }
+
+    // Row-level bookkeeping, run by exactly one warp per CTA per row.
+    // lazy (lookup in a cluster): only publish this CTA's total and local prefixes; whoever needs the row-wide
+    // numbers (the one owner warp) waits for the peers itself, so this warp is not held up.
+    static __device__ __noinline__ void finish_row(int V, uint32_t par, bool dec_mode, bool lazy) {
         const int ln = lane();
         fence_acq_rel_cta();
         const uint64_t v = *reinterpret_cast<volatile uint64_t*>(&g_ctl.wsum[ln]);
         const uint64_t inc = warp_incl_scan(v, ln);
-        const uint64_t Q = __shfl_sync(0xffffffffu, inc, 31);
-        const uint64_t exc = inc - v;
+        uint64_t Q = __shfl_sync(0xffffffffu, inc, 31);
+        uint64_t base = 0;
+        if (CL > 1) {  // exchange the CTA totals; base = total of the lower-ranked CTAs
+            if (ln < CL) {
+                st_cluster_u64(mapa(smem_u32(&g_ctl.cl_Q[par][Clu<CL>::rank()]), ln), Q);
+                mbar_arrive_cluster(mapa(smem_u32(&g_ctl.cl_sum_bar), ln));
+            }
+            if (lazy) {
+                g_ctl.pref[ln] = inc - v;  // CTA-local prefix; row_totals() adds the lower CTAs
+                __syncwarp();
+                if (ln == 0) {
+                    g_ctl.arrive = 0;
+                    mbar_arrive(&g_ctl.done);
+                }
+                return;
+            }
+            mbar_wait_cluster(&g_ctl.cl_sum_bar, par);
+            uint64_t tot = 0;
+#pragma unroll
+            for (int p = 0; p < CL; p++) {
+                const uint64_t qp = g_ctl.cl_Q[par][p];
+                if (p < (int)Clu<CL>::rank()) base += qp;
+                tot += qp;
+            }
+            Q = tot;
+        }
+        const uint64_t exc = base + inc - v;  // row-wide exclusive prefix at the start of local warp `ln`
         g_ctl.pref[ln] = exc;
         lq::Scale sc;
         sc.Q = Q;
@@ -364,12 +492,22 @@ struct RowEngine {
         if (ln == 0) sc = lq::make_scale(Q, V);
         sc.R = __shfl_sync(0xffffffffu, sc.R, 0);
         sc.s = __shfl_sync(0xffffffffu, sc.s, 0);
-        if (dec) {  // lane w tests warp w's segment start: the owner is the last non-empty one at or below the value
-            const int gb = seg_begin(ln, V), ge = seg_begin(ln + 1, V);
-            const uint64_t w = (uint64_t)(dec->high - dec->low + 1), xr = (uint64_t)(dec->value - dec->low);
+        if (dec_mode) {
+            // lane w tests the start of local warp w; the owner is the last non-empty segment of the whole row
+            // whose start is at or below the value, so this CTA owns it unless the next CTA's start qualifies too
+            const int64_t low = (int64_t)dec_ld(par, 0), high = (int64_t)dec_ld(par, 1), value = (int64_t)dec_ld(par, 2);
+            const uint64_t w = (uint64_t)(high - low + 1), xr = (uint64_t)(value - low);
+            const int gw = (int)Clu<CL>::rank() * kWarps + ln;
+            const int gb = seg_begin(gw, V), ge = seg_begin(gw + 1, V);
             const bool ok = gb < ge && coder::scale32_ceil(lq::cum_of(exc, (uint32_t)(gb * VEC), sc), w) <= xr;
             const unsigned ball = __ballot_sync(0xffffffffu, ok);
-            if (ln == 0) g_ctl.owner = 31 - __clz((int)ball);
+            int owner = ball ? 31 - __clz((int)ball) : -1;
+            if (CL > 1 && Clu<CL>::rank() + 1 < CL) {
+                const int nb = seg_begin(((int)Clu<CL>::rank() + 1) * kWarps, V);  // first group of the next CTA
+                const uint64_t nexc = base + __shfl_sync(0xffffffffu, inc, 31);
+                if (nb < groups(V) && coder::scale32_ceil(lq::cum_of(nexc, (uint32_t)(nb * VEC), sc), w) <= xr) owner = -1;
+            }
+            if (ln == 0) g_ctl.owner = owner;
         }
         __syncwarp();
         if (ln == 0) {
@@ -379,6 +517,21 @@ struct RowEngine {
             g_ctl.arrive = 0;
             mbar_arrive(&g_ctl.done);  // release: publishes everything above
         }
+    }
+    // Lazy mode, called by one lane after wait_done(): row total, this CTA's base, and the scale.
+    __device__ __forceinline__ lq::Scale row_totals(int V, uint64_t& base) const {
+        base = 0;
+        if (CL == 1) return scale();
+        const uint32_t par = (it - 1) & 1;
+        mbar_wait_cluster(&g_ctl.cl_sum_bar, par);
+        uint64_t tot = 0;
+#pragma unroll
+        for (int p = 0; p < CL; p++) {
+            const uint64_t qp = g_ctl.cl_Q[par][p];
+            if (p < (int)Clu<CL>::rank()) base += qp;
+            tot += qp;
+        }
+        return lq::make_scale(tot, V);
     }
     // Block until the row-level results of the row just reduce()d are published.
     __device__ __forceinline__ void wait_done() const { mbar_wait(&g_ctl.done, (it - 1) & 1); }
@@ -392,27 +545,28 @@ struct RowEngine {
 };
 
 // ------------------------------------------------------------------ LOOKUP
-template <int VEC, bool TMA, int NCH>
+template <int VEC, bool TMA, int NCH, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 lookup_kernel(const __grid_constant__ RowParams rp, int V, const int32_t* __restrict__ syms,
               uint32_t* __restrict__ pairs, uint32_t* __restrict__ status) {
-    using Eng = RowEngine<VEC, TMA, NCH>;
+    using Eng = RowEngine<VEC, TMA, NCH, CL>;
     Ctl& ctl = g_ctl;
     Eng eng;
     eng.setup();
+    const uint32_t stride = Clu<CL>::count();
     RowSeq seq;
-    seq.init(rp);
+    seq.init(rp, Clu<CL>::id(), stride);
     if (seq.valid(rp)) Eng::issue(seq.ptr(rp), V);
     while (seq.valid(rp)) {
         const int64_t r = seq.s;
         const float* row = seq.ptr(rp);
         const int sym = __ldg(syms + r);  // issued now, consumed after the row's compute phases
-        seq.next(rp);
+        seq.next(rp, stride);
         uint32_t q[kPerThread];
-        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, V, q);
+        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, V, q, false, CL > 1);
         const int warp = Eng::warp(), lane = Eng::lane(), gbeg = Eng::gbeg(V), gend = Eng::gend(V);
         if (sym < 0 || sym >= V) {
-            if (threadIdx.x == 0) {
+            if (threadIdx.x == 0 && Clu<CL>::rank() == 0) {
                 *reinterpret_cast<uint2*>(pairs + 2 * r) = make_uint2(0u, 0u);
                 if (status) atomicOr(status + r, LAC_ST_SYMBOL);
             }
@@ -436,8 +590,9 @@ lookup_kernel(const __grid_constant__ RowParams rp, int V, const int32_t* __rest
             qs = warp_sum48(qs);
             eng.wait_done();
             if (lane == 0) {
-                const lq::Scale sc = Eng::scale();
-                const uint64_t C = ctl.pref[warp] + part;
+                uint64_t base;
+                const lq::Scale sc = eng.row_totals(V, base);
+                const uint64_t C = base + ctl.pref[warp] + part;
                 uint2 o;
                 o.x = lq::cum_of(C, (uint32_t)sym, sc);
                 o.y = (sym == V - 1) ? 0u : lq::cum_of(C + qs, (uint32_t)sym + 1, sc);
@@ -446,23 +601,25 @@ lookup_kernel(const __grid_constant__ RowParams rp, int V, const int32_t* __rest
             __syncwarp();
         }
     }
+    Eng::teardown();
 }
 
 // ------------------------------------------------------------------ BUILD
-template <int VEC, bool TMA, int NCH>
+template <int VEC, bool TMA, int NCH, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 build_kernel(const __grid_constant__ RowParams rp, int V, uint32_t* __restrict__ cum) {
-    using Eng = RowEngine<VEC, TMA, NCH>;
+    using Eng = RowEngine<VEC, TMA, NCH, CL>;
     Ctl& ctl = g_ctl;
     Eng eng;
     eng.setup();
+    const uint32_t stride = Clu<CL>::count();
     RowSeq seq;
-    seq.init(rp);
+    seq.init(rp, Clu<CL>::id(), stride);
     if (seq.valid(rp)) Eng::issue(seq.ptr(rp), V);
     while (seq.valid(rp)) {
         const int64_t r = seq.s;
         const float* row = seq.ptr(rp);
-        seq.next(rp);
+        seq.next(rp, stride);
         uint32_t q[kPerThread];
         eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, V, q);
         const int warp = Eng::warp(), lane = Eng::lane(), gbeg = Eng::gbeg(V), gend = Eng::gend(V);
@@ -497,6 +654,7 @@ build_kernel(const __grid_constant__ RowParams rp, int V, uint32_t* __restrict__
             }
         }
     }
+    Eng::teardown();
 }
 
 // ------------------------------------------------------------------ DECODE
@@ -519,7 +677,6 @@ __device__ __forceinline__ void dec_load_state(DecShared& d, const lac_dec_state
     d.high = st[s].high;
     d.value = st[s].value;
     d.pos = st[s].pos;
-    d.status = st[s].status;
     d.data_off = offsets[s];
     d.nbytes = (uint64_t)(offsets[s + 1] - offsets[s]);
     d.win_byte = d.pos >> 3;
@@ -527,88 +684,83 @@ __device__ __forceinline__ void dec_load_state(DecShared& d, const lac_dec_state
     d.win_lo = load_be64(bytes + d.data_off, d.nbytes, d.win_byte + 8);
 }
 
-template <int VEC, bool TMA, int NCH>
+template <int VEC, bool TMA, int NCH, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 decode_kernel(const __grid_constant__ RowParams rp, int V, lac_dec_state* __restrict__ state,
               const uint8_t* __restrict__ bytes, const int64_t* __restrict__ offsets,
               int32_t* __restrict__ syms, int64_t sym_stride, int P) {
-    using Eng = RowEngine<VEC, TMA, NCH>;
+    using Eng = RowEngine<VEC, TMA, NCH, CL>;
     Ctl& ctl = g_ctl;
     Eng eng;
     eng.setup();
     constexpr int IT = kPerThread / VEC;
+    const uint32_t stride = Clu<CL>::count();
     RowSeq seq;
-    seq.init(rp);
+    seq.init(rp, Clu<CL>::id(), stride);
     if (seq.valid(rp)) Eng::issue(seq.ptr(rp), V);
-    uint32_t par = 0;  // which DecShared buffer the current stream uses
     while (seq.valid(rp)) {
         const int64_t s = seq.s;
         const int t = seq.t;
         const bool first = (t == 0), last = (t == seq.Ts - 1);
         const float* row = seq.ptr(rp);
-        seq.next(rp);
-        if (first) {
-            // double-buffered by stream parity: the previous stream's owner lane may still be
-            // finishing with the other buffer; published by the block barrier inside reduce()
-            par ^= 1;
-            if (threadIdx.x == 0) dec_load_state(ctl.dec[par], state, bytes, offsets, s);
-        }
+        seq.next(rp, stride);
+        // The decoder state of row `it` sits in dec[it & 1] of rank 0; the owner lane of this row writes the
+        // state of the next row into dec[(it + 1) & 1].  A new stream's state is loaded before the row's block
+        // barrier; it reaches the other CTAs through the release / acquire chain of the totals exchange.
+        const uint32_t cur = eng.it & 1;
+        if (first && threadIdx.x == 0 && Clu<CL>::rank() == 0) dec_load_state(ctl.dec[cur], state, bytes, offsets, s);
         uint32_t q[kPerThread];
-        DecShared& dec = ctl.dec[par];
-        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, V, q, &dec);
+        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, V, q, true);
         eng.wait_done();
         const int warp = Eng::warp(), lane = Eng::lane(), gbeg = Eng::gbeg(V), gend = Eng::gend(V);
         if (warp == ctl.owner) {
-            const uint64_t w = (uint64_t)(dec.high - dec.low + 1);
-            const uint64_t xr = (uint64_t)(dec.value - dec.low);
+            const int64_t low = (int64_t)Eng::dec_ld(cur, 0), high = (int64_t)Eng::dec_ld(cur, 1);
+            const int64_t value = (int64_t)Eng::dec_ld(cur, 2);
+            const uint64_t w = (uint64_t)(high - low + 1);
+            const uint64_t xr = (uint64_t)(value - low);
             const lq::Scale sc = Eng::scale();
             const uint64_t Cb = ctl.pref[warp];
-            // ---- owner warp: IT interleaved lane scans of the group sums, then one ballot per slab.
-            // Groups are ordered (slab k, lane); cum is monotone in that order, so the number of groups
-            // at or below the value identifies the owner, and for the owning lane the last slab in which
-            // its own group qualified is the owning slab.
-            uint64_t inc[IT];
+            // ---- owner warp, three levels: slab (32 groups = 128 elements), lane, element.
+            // cum is monotone in index order, so at every level the owner is the LAST boundary at or below
+            // the value.  Slab totals come from REDUX (independent, pipelined); only the chosen slab is scanned.
+            uint32_t gs[IT];
 #pragma unroll
             for (int k = 0; k < IT; k++) {
-                uint64_t a = 0;
+                uint32_t a = 0;  // VEC q values < 2^29.5 each: no overflow
 #pragma unroll
                 for (int e = 0; e < VEC; e++) a += q[k * VEC + e];
-                inc[k] = a;
+                gs[k] = a;
             }
+            uint64_t base = Cb, Csel = Cb;
+            int ksel = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-                for (int k = 0; k < IT; k++) {
-                    uint64_t v = __shfl_up_sync(0xffffffffu, inc[k], o);
-                    if (lane >= o) inc[k] += v;
+            for (int k = 0; k < IT; k++) {
+                const int g0 = gbeg + k * 32;
+                if (g0 < gend && cum_le(lq::cum_of(base, (uint32_t)(g0 * VEC), sc), xr, w)) {
+                    ksel = k;
+                    Csel = base;
                 }
+                base += warp_sum48((uint64_t)gs[k]);
             }
-            uint64_t base = Cb, C = 0;
-            int cnt = 0, ksel = 0;
-            uint32_t qe[VEC];
+            uint32_t gsel = 0, qe[VEC];
 #pragma unroll
             for (int e = 0; e < VEC; e++) qe[e] = 0;
 #pragma unroll
             for (int k = 0; k < IT; k++) {
-                uint64_t a = 0;
-#pragma unroll
-                for (int e = 0; e < VEC; e++) a += q[k * VEC + e];
-                const uint64_t Cg = base + inc[k] - a;
-                base += __shfl_sync(0xffffffffu, inc[k], 31);
-                const int gk = gbeg + k * 32 + lane;
-                const bool ok = gk < gend && cum_le(lq::cum_of(Cg, (uint32_t)(gk * VEC), sc), xr, w);
-                cnt += __popc(__ballot_sync(0xffffffffu, ok));
-                if (ok) {
-                    C = Cg;
-                    ksel = k;
+                if (k == ksel) {  // warp-uniform
+                    gsel = gs[k];
 #pragma unroll
                     for (int e = 0; e < VEC; e++) qe[e] = q[k * VEC + e];
                 }
             }
-            const int j = cnt - 1;  // ordinal of the owning group in (slab, lane) order
-            if (lane == (j & 31)) {
+            const uint64_t inc = warp_incl_scan((uint64_t)gsel, lane);
+            const uint64_t C = Csel + inc - gsel;
+            const int gl = gbeg + ksel * 32 + lane;
+            const bool ok = gl < gend && cum_le(lq::cum_of(C, (uint32_t)(gl * VEC), sc), xr, w);
+            const unsigned ball = __ballot_sync(0xffffffffu, ok);
+            if (lane == 31 - __clz((int)ball)) {
                 // ---- element level (one lane)
-                const int g = gbeg + ksel * 32 + lane;
+                const int g = gl;
                 int sym = g * VEC;
                 uint64_t Cs = C, Ce = C;
                 uint32_t qsym = qe[0];
@@ -624,15 +776,14 @@ decode_kernel(const __grid_constant__ RowParams rp, int V, lac_dec_state* __rest
                 const uint32_t lo = lq::cum_of(Cs, (uint32_t)sym, sc);
                 const uint32_t hi = (sym == V - 1) ? 0u : lq::cum_of(Cs + qsym, (uint32_t)sym + 1, sc);
                 // ---- A_from_bin.emit_symbol + emit_bit loop (arith_code.py:278-298)
-                int64_t nl = dec.low, nh = dec.high;
-                const int64_t value = dec.value;
+                int64_t nl = low, nh = high;
                 coder::ac_narrow32(nl, nh, lo, hi);
                 const int64_t off = value - nl;  // the value stays inside [nl, nh]
                 const int k = coder::renorm_count((uint64_t)(nh - nl + 1), P);
                 coder::renorm_apply(nl, nh, P, k);
                 // next k bits from the 128-bit window (k <= 60, window offset < 64)
-                const uint64_t pos = dec.pos;
-                const uint64_t hi64 = dec.win_hi, lo64 = dec.win_lo, wb = dec.win_byte;
+                const uint64_t pos = Eng::dec_ld(cur, 3);
+                const uint64_t hi64 = Eng::dec_ld(cur, 4), lo64 = Eng::dec_ld(cur, 5), wb = Eng::dec_ld(cur, 6);
                 const int o = (int)(pos - (wb << 3));
                 const uint64_t comb = o ? ((hi64 << o) | (lo64 >> (64 - o))) : hi64;
                 const uint64_t nb = k ? (comb >> (64 - k)) : 0;
@@ -644,20 +795,30 @@ decode_kernel(const __grid_constant__ RowParams rp, int V, lac_dec_state* __rest
                     state[s].value = nv;
                     state[s].pos = pos + (uint64_t)k;
                 } else {
-                    dec.low = nl;
-                    dec.high = nh;
-                    dec.value = nv;
-                    dec.pos = pos + (uint64_t)k;
+                    const uint32_t nxt = cur ^ 1;
+                    const int64_t data_off = (int64_t)Eng::dec_ld(cur, 7);
+                    const uint64_t nbytes = Eng::dec_ld(cur, 8);
+                    Eng::dec_st(nxt, 0, (uint64_t)nl);
+                    Eng::dec_st(nxt, 1, (uint64_t)nh);
+                    Eng::dec_st(nxt, 2, (uint64_t)nv);
+                    Eng::dec_st(nxt, 3, pos + (uint64_t)k);
                     if (o + k >= 64) {  // slide the window by 8 bytes
-                        dec.win_hi = lo64;
-                        dec.win_byte = wb + 8;
-                        dec.win_lo = load_be64(bytes + dec.data_off, dec.nbytes, wb + 16);
+                        Eng::dec_st(nxt, 4, lo64);
+                        Eng::dec_st(nxt, 5, load_be64(bytes + data_off, nbytes, wb + 16));
+                        Eng::dec_st(nxt, 6, wb + 8);
+                    } else {
+                        Eng::dec_st(nxt, 4, hi64);
+                        Eng::dec_st(nxt, 5, lo64);
+                        Eng::dec_st(nxt, 6, wb);
                     }
+                    Eng::dec_st(nxt, 7, (uint64_t)data_off);
+                    Eng::dec_st(nxt, 8, nbytes);
                 }
             }
             __syncwarp();
         }
     }
+    Eng::teardown();
 }
 
 __global__ void dec_init_kernel(lac_dec_state* state, int64_t n, int P, const uint8_t* bytes,
@@ -675,17 +836,22 @@ __global__ void dec_init_kernel(lac_dec_state* state, int64_t n, int P, const ui
 }
 
 // ------------------------------------------------------------------ launchers
-static int grid_for(int64_t units) {
+static int sm_count() {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return (int)(units < sms ? (units > 0 ? units : 1) : sms);
+    return sms;
 }
 
-// 0: scalar LDG (any alignment), 1: 128-bit LDG, 2 / 4 / 8: TMA bulk ring with that many chunks per row
-// (default 2 when rows are 16-byte aligned; LAC_NO_TMA=1 and LAC_TMA_CHUNKS=n are measurement switches)
-static int path_for(const float* p, int V, int64_t s0, int64_t s1) {
-    bool v4 = (V % 4 == 0) && ((((uintptr_t)p) & 15) == 0) && (s0 % 4 == 0) && (s1 % 4 == 0);
+// Path selection.  Returns cluster size CL (1, 2, 4, 8) in *cl and the staging path:
+// 0: scalar LDG (any alignment, CL = 1), 1: 128-bit LDG (CL = 1), 2 / 4 / 8: TMA bulk ring with that many chunks
+// per row and CTA (default 2; LAC_NO_TMA=1 and LAC_TMA_CHUNKS=n are measurement switches).  -1: unsupported.
+static int path_for(const float* p, int V, int64_t s0, int64_t s1, int* cl) {
+    const bool v4 = (V % 4 == 0) && ((((uintptr_t)p) & 15) == 0) && (s0 % 4 == 0) && (s1 % 4 == 0);
+    const int cap = kThreads * kPerThread;
+    *cl = V <= cap ? 1 : V <= 2 * cap ? 2 : V <= 4 * cap ? 4 : 8;
+    if (V > 8 * cap) return -1;
+    if (*cl > 1) return v4 ? 2 : -1;  // rows split over a cluster need 16-byte aligned rows
     if (!v4) return 0;
     static const bool no_tma = getenv("LAC_NO_TMA") != nullptr;
     if (no_tma) return 1;
@@ -693,42 +859,74 @@ static int path_for(const float* p, int V, int64_t s0, int64_t s1) {
     return (nch == 4 || nch == 8) ? nch : 2;
 }
 
-template <typename K, typename... A>
-static cudaError_t launch_tma(K kernel, int ring_bytes, int grid, cudaStream_t st, A... args) {
+template <int CL, typename K, typename... A>
+static cudaError_t launch_tma(K kernel, int ring_bytes, int64_t units, cudaStream_t st, A... args) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes);
     if (e != cudaSuccess) return e;
-    kernel<<<grid, kThreads, ring_bytes, st>>>(args...);
-    return cudaGetLastError();
+    if (CL > 1) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)ring_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int clusters = sm_count() / CL;
+    if (CL > 1) {  // persistent kernel: exactly as many clusters as can be co-resident
+        cfg.gridDim = dim3((unsigned)(clusters * CL));
+        int n = 0;
+        e = cudaOccupancyMaxActiveClusters(&n, kernel, &cfg);
+        if (e != cudaSuccess) return e;
+        if (n < 1) return cudaErrorLaunchOutOfResources;
+        if (n < clusters) clusters = n;
+    }
+    if (units < clusters) clusters = (int)(units > 0 ? units : 1);
+    cfg.gridDim = dim3((unsigned)(clusters * CL));
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
+
+static int plain_grid(int64_t units) {
+    int sms = sm_count();
+    return (int)(units < sms ? (units > 0 ? units : 1) : sms);
+}
+
+#define LAC_DISPATCH(KERNEL, UNITS, ...)                                                                              \
+    switch (cl * 16 + path) {                                                                                         \
+        case 16 + 2: return launch_tma<1>(KERNEL<4, true, 2, 1>, Ring<2>::kRingBytes, UNITS, st, __VA_ARGS__);        \
+        case 16 + 4: return launch_tma<1>(KERNEL<4, true, 4, 1>, Ring<4>::kRingBytes, UNITS, st, __VA_ARGS__);        \
+        case 16 + 8: return launch_tma<1>(KERNEL<4, true, 8, 1>, Ring<8>::kRingBytes, UNITS, st, __VA_ARGS__);        \
+        case 32 + 2: return launch_tma<2>(KERNEL<4, true, 2, 2>, Ring<2>::kRingBytes, UNITS, st, __VA_ARGS__);        \
+        case 64 + 2: return launch_tma<4>(KERNEL<4, true, 2, 4>, Ring<2>::kRingBytes, UNITS, st, __VA_ARGS__);        \
+        case 128 + 2: return launch_tma<8>(KERNEL<4, true, 2, 8>, Ring<2>::kRingBytes, UNITS, st, __VA_ARGS__);       \
+        case 16 + 1: KERNEL<4, false, 8, 1><<<plain_grid(UNITS), kThreads, 0, st>>>(__VA_ARGS__); break;              \
+        case 16 + 0: KERNEL<1, false, 8, 1><<<plain_grid(UNITS), kThreads, 0, st>>>(__VA_ARGS__); break;              \
+        default: return cudaErrorInvalidValue;                                                                        \
+    }                                                                                                                 \
+    return cudaGetLastError();
 
 cudaError_t launch_lookup(const float* logits, int64_t rows, int V, int64_t row_stride, const int32_t* syms,
                           uint32_t* pairs, uint32_t* status, cudaStream_t st) {
     if (rows == 0) return cudaSuccess;
-    int grid = grid_for(rows);
     const RowParams rp{logits, rows, 1, row_stride, 0, nullptr};
-    switch (path_for(logits, V, row_stride, 0)) {
-        case 2: return launch_tma(lookup_kernel<4, true, 2>, Ring<2>::kRingBytes, grid, st, rp, V, syms, pairs, status);
-        case 4: return launch_tma(lookup_kernel<4, true, 4>, Ring<4>::kRingBytes, grid, st, rp, V, syms, pairs, status);
-        case 8: return launch_tma(lookup_kernel<4, true, 8>, Ring<8>::kRingBytes, grid, st, rp, V, syms, pairs, status);
-        case 1: lookup_kernel<4, false, 8><<<grid, kThreads, 0, st>>>(rp, V, syms, pairs, status); break;
-        default: lookup_kernel<1, false, 8><<<grid, kThreads, 0, st>>>(rp, V, syms, pairs, status);
-    }
-    return cudaGetLastError();
+    int cl = 1;
+    const int path = path_for(logits, V, row_stride, 0, &cl);
+    LAC_DISPATCH(lookup_kernel, rows, rp, V, syms, pairs, status)
 }
 
 cudaError_t launch_build(const float* logits, int64_t rows, int V, int64_t row_stride, uint32_t* cum,
                          cudaStream_t st) {
     if (rows == 0) return cudaSuccess;
-    int grid = grid_for(rows);
     const RowParams rp{logits, rows, 1, row_stride, 0, nullptr};
-    switch (path_for(logits, V, row_stride, 0)) {
-        case 2: return launch_tma(build_kernel<4, true, 2>, Ring<2>::kRingBytes, grid, st, rp, V, cum);
-        case 4: return launch_tma(build_kernel<4, true, 4>, Ring<4>::kRingBytes, grid, st, rp, V, cum);
-        case 8: return launch_tma(build_kernel<4, true, 8>, Ring<8>::kRingBytes, grid, st, rp, V, cum);
-        case 1: build_kernel<4, false, 8><<<grid, kThreads, 0, st>>>(rp, V, cum); break;
-        default: build_kernel<1, false, 8><<<grid, kThreads, 0, st>>>(rp, V, cum);
-    }
-    return cudaGetLastError();
+    int cl = 1;
+    const int path = path_for(logits, V, row_stride, 0, &cl);
+    LAC_DISPATCH(build_kernel, rows, rp, V, cum)
 }
 
 cudaError_t launch_decode(const float* logits, int64_t n_streams, int64_t T, int64_t stream_stride,
@@ -736,16 +934,10 @@ cudaError_t launch_decode(const float* logits, int64_t n_streams, int64_t T, int
                           const uint8_t* bytes, const int64_t* offsets, int32_t* syms, int64_t sym_stride,
                           int P, cudaStream_t st) {
     if (n_streams == 0 || T == 0) return cudaSuccess;
-    int grid = grid_for(n_streams);
     const RowParams rp{logits, n_streams, T, stream_stride, tok_stride, ntok};
-    switch (path_for(logits, V, stream_stride, tok_stride)) {
-        case 2: return launch_tma(decode_kernel<4, true, 2>, Ring<2>::kRingBytes, grid, st, rp, V, state, bytes, offsets, syms, sym_stride, P);
-        case 4: return launch_tma(decode_kernel<4, true, 4>, Ring<4>::kRingBytes, grid, st, rp, V, state, bytes, offsets, syms, sym_stride, P);
-        case 8: return launch_tma(decode_kernel<4, true, 8>, Ring<8>::kRingBytes, grid, st, rp, V, state, bytes, offsets, syms, sym_stride, P);
-        case 1: decode_kernel<4, false, 8><<<grid, kThreads, 0, st>>>(rp, V, state, bytes, offsets, syms, sym_stride, P); break;
-        default: decode_kernel<1, false, 8><<<grid, kThreads, 0, st>>>(rp, V, state, bytes, offsets, syms, sym_stride, P);
-    }
-    return cudaGetLastError();
+    int cl = 1;
+    const int path = path_for(logits, V, stream_stride, tok_stride, &cl);
+    LAC_DISPATCH(decode_kernel, n_streams, rp, V, state, bytes, offsets, syms, sym_stride, P)
 }
 
 cudaError_t launch_dec_init(lac_dec_state* state, int64_t n, int P, const uint8_t* bytes,
@@ -755,6 +947,8 @@ cudaError_t launch_dec_init(lac_dec_state* state, int64_t n, int P, const uint8_
     return cudaGetLastError();
 }
 
+// Largest vocabulary the CDF kernels take; rows_need_alignment: above one CTA's capacity rows must be 16-byte aligned.
+int max_vocab() { return 8 * kThreads * kPerThread; }
 int max_vocab_single_cta() { return kThreads * kPerThread; }
 
 }  // namespace lac

@@ -62,6 +62,45 @@ def test_cdf_build_bit_exact(V):
     assert (np.diff(full, axis=1) >= 1).all()
 
 
+@pytest.mark.parametrize("V", [32772, 50000, 65536, 65540, 128256, 131072, 151936, 262144])
+def test_cluster_rows_bit_exact(V):
+    """Vocabularies wider than one CTA (32768): the row is split over a 2 / 4 / 8-CTA cluster."""
+    rng = np.random.default_rng(V)
+    logits = _special_rows(V, rng)[:9]
+    logits = np.concatenate([logits, (rng.standard_normal((5, V)) * 6).astype(np.float32)])
+    got = coder.cdf_build(_dev(logits)).cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, orc.lq32_cdf(logits))
+    syms = rng.integers(0, V, len(logits)).astype(np.int32)
+    syms[:4] = [0, V - 1, V // 2, 32768]
+    lo, hi = orc.lq32_lookup(logits, syms)
+    pairs = coder.cdf_lookup(_dev(logits), _dev(syms)).cpu().numpy().view(np.uint32)
+    assert np.array_equal(pairs[:, 0], lo)
+    assert np.array_equal(pairs[:, 1].astype(np.uint64), hi & 0xFFFFFFFF)
+
+
+@pytest.mark.parametrize("V,S,T", [(128256, 6, 12), (65536, 40, 5), (262144, 3, 7)])
+def test_cluster_encode_decode_roundtrip(V, S, T):
+    rng = np.random.default_rng(V + S)
+    logits = (rng.standard_normal((S, T, V)) * 5).astype(np.float32)
+    syms = rng.integers(0, V, (S, T)).astype(np.int32)
+    syms[0, :3] = [0, V - 1, 40000]
+    dl = _dev(logits)
+    enc = coder.StreamEncoder(S, capacity_bytes=T * 8 + 64)
+    enc.encode_logits(dl, _dev(syms), finish=True)
+    streams, _ = enc.bitstreams()
+    for s in range(min(S, 3)):
+        assert streams[s] == _oracle_stream(logits[s], syms[s], 48)
+    assert np.array_equal(coder.StreamDecoder(streams).decode_logits(dl).cpu().numpy(), syms)
+    dec = coder.StreamDecoder(streams)
+    step = torch.stack([dec.decode_step(dl[:, t].contiguous()) for t in range(T)], dim=1).cpu().numpy()
+    assert np.array_equal(step, syms)
+
+
+def test_wide_unaligned_vocab_is_rejected():
+    with pytest.raises(_ffi.LacError):
+        coder.cdf_build(torch.zeros((2, 40001), dtype=torch.float32, device="cuda"))
+
+
 def test_cdf_build_unaligned_rows_use_scalar_path():
     rng = np.random.default_rng(5)
     V = 1001  # odd vocab: rows are not 16-byte aligned
