@@ -1,0 +1,126 @@
+"""The reference-facing Python API (same names as arith_code.py / arithmetic_coding.py /
+llama_compress.py).  CPU part: table walking and bit packing.  GPU part: the mirrors produce the
+reference's golden bits."""
+import os
+
+import numpy as np
+import pytest
+
+from lac_b200 import arith_code as ac
+from lac_b200 import arithmetic_coding as acs
+
+
+class AdaptiveCounts(ac.ProbPredictor):
+    """Same 'simple adaptive frequency model' the goldens were made with (tests/golden/make_golden.py)."""
+
+    def __init__(self, n, counts=None):
+        super().__init__(n)
+        self.counts = [0] * n if counts is None else counts
+
+    def prob(self, symbol):
+        return 1 + self.counts[symbol]
+
+    def accept(self, symbol):
+        self.counts[symbol] += 1
+        return super().accept(symbol)
+
+    def copy(self):
+        return AdaptiveCounts(self.n, list(self.counts))
+
+
+def test_materialise_tables_walks_like_receive_symbol():
+    dist, minp = ac.materialise_tables(AdaptiveCounts(4), [2, 2, 0])
+    assert dist.tolist() == [[1, 2, 3, 4], [1, 2, 4, 5], [1, 2, 5, 6]]
+    assert minp.tolist() == [1, 1, 1]
+    d, m = ac.materialise_tables(ac.CDFPredictor([3, 5, 6, 10]), [0, 3])
+    assert d.tolist() == [[3, 5, 6, 10]] * 2 and m.tolist() == [1, 1]
+
+
+def test_bit_packing_matches_reference_layout():
+    from oracle import oracle as orc
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 7, 8, 9, 77):
+        bits = rng.integers(0, 2, n).tolist()
+        assert bytes(ac.group_bits(bits)) == orc.pack_bits(np.array(bits, dtype=np.uint8)).tobytes()
+        assert list(ac.ungroup_bits(bytes(ac.group_bits(bits))))[:n] == bits
+        out = bytearray()
+        pk = acs.packbits(out.append)
+        for b in bits:
+            pk(b)
+        pk.flush()
+        assert bytes(out) == bytes(ac.group_bits(bits))
+        assert list(acs.unpackbits(out))[:n] == bits
+
+
+def test_scaled_cdf_is_the_reference_expression():
+    from oracle import ref_quant
+    p = np.random.default_rng(1).dirichlet(np.ones(50))
+    assert np.array_equal(acs.ACSampler(48).scaled_cdf(p), ref_quant.acs_cdf(p, 48))
+
+
+# ------------------------------------------------------------------ GPU
+torch = pytest.importorskip("torch")
+gpu = pytest.mark.gpu
+needs_gpu = pytest.mark.skipif(not torch.cuda.is_available(), reason="no CUDA device")
+
+
+@gpu
+@needs_gpu
+def test_mirror_ac_on_goldens(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ac_small.npz"))
+    names = list(g["names"])[::9]
+    for nm in names:
+        prec, stop = int(g[f"{nm}/prec"]), int(g[f"{nm}/stop"])
+        dist, syms = [int(x) for x in g[f"{nm}/dist"]], [int(x) for x in g[f"{nm}/syms"]]
+        coder_ = ac.AC(ac.CDFPredictor(dist), prec)
+        want = [int(b) for b in g[f"{nm}/bits"]]
+        assert list(coder_.to_bin.bits(syms, stop)) == want, nm
+        r, n = coder_.to_bin.encode(syms, stop)
+        assert n == len(want) and r == int("0" + "".join(map(str, want)), 2)
+        if stop and syms:
+            assert list(coder_.from_bin.run(want, stop, count=len(syms))) == syms, nm
+
+
+@gpu
+@needs_gpu
+def test_mirror_adaptive_model_matches_reference_bytes(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ac_adaptive.npz"))
+    data = g["data"].tolist()
+    coder_ = ac.AC(AdaptiveCounts(256), int(g["prec"]))
+    comp = coder_.to_bin.compress(data)
+    assert comp == g["comp"].tobytes()
+    head = coder_.from_bin.decompress(comp, 300)   # adaptive decode is one GPU call per symbol
+    assert head == data[:300]
+
+
+@gpu
+@needs_gpu
+def test_mirror_acsampler_on_goldens(golden_dir):
+    g = np.load(os.path.join(golden_dir, "acs_small.npz"))
+    from oracle import oracle as orc
+    for nm in list(g["names"])[::3]:
+        prec, cdf, toks = int(g[f"{nm}/prec"]), g[f"{nm}/cdf"], g[f"{nm}/toks"].tolist()
+        s = acs.ACSampler(prec)
+        assert s.compress(cdf, toks) == orc.pack_bits(g[f"{nm}/bits"]).tobytes()
+        assert s.last_nbits == len(g[f"{nm}/bits"])
+        assert s.expand(cdf, s.compress(cdf, toks, flush="safe"), len(toks)) == toks
+
+
+@gpu
+@needs_gpu
+def test_llama_compress_roundtrip_and_size():
+    """configs[2] in miniature: Llama-style random-init model, vocab 32000, ragged chunks, container."""
+    from lac_b200 import container, llama_compress as lc
+    vocab, chunk = 32000, 24
+    model = lc.TinyLlama(vocab=vocab, dim=64, layers=2, heads=4, max_len=chunk + 1, seed=3).cuda()
+    rng = np.random.default_rng(5)
+    toks = rng.integers(0, vocab, 5 * chunk + 7).astype(np.int32)
+    comp = lc.LlamaCompressor(model, vocab, chunk_tokens=chunk, max_streams=4)
+    blob = comp.compress(toks)
+    c = container.unpack(blob)
+    assert c.n_chunks == 6 and c.ntok.tolist() == [chunk] * 5 + [7]
+    back = comp.decompress(blob)
+    assert np.array_equal(back, toks)
+    # random tokens under a random-init model (logit std ~4) cost log2(V) + sigma^2 / (2 ln 2) ~ 26 bits each
+    bits = float(c.nbits.sum())
+    assert 0.9 * np.log2(vocab) * len(toks) < bits < 2.5 * np.log2(vocab) * len(toks)
