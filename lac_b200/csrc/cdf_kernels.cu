@@ -235,8 +235,10 @@ struct Ctl {
     uint32_t R;                 // lq::Scale                               } `done` flips
     int s;                      //                                         }
     int owner;                  // decode: local warp whose segment holds the symbol, or -1
+    uint32_t target;            // decode: floor(((value - low) << 32) / (high - low + 1)), val_to_symbol's probe
     uint32_t arrive;            // warps done with phase B of the current row
     DecShared dec[2];           // decoder state (rank 0's copy is the live one), double-buffered by row parity
+    __align__(16) uint32_t xpose[kWarps * 32 + 4 * 32];  // decode owner warp: q values on their way to lane-major order (padded)
 };
 
 // Rows visited by this CTA / cluster, in order: outer index s = first, += stride; inner t < Ts.
@@ -485,29 +487,47 @@ struct RowEngine {
         }
         const uint64_t exc = base + inc - v;  // row-wide exclusive prefix at the start of local warp `ln`
         g_ctl.pref[ln] = exc;
+        // The two divisions of the row run side by side: lane 0 the scale R = floor(N / D), lane 1 (decode) the
+        // probe of val_to_symbol, target = floor(((value - low) << 32) / w) (arith_code.py:94-101 with d = 2^32).
         lq::Scale sc;
         sc.Q = Q;
         sc.R = 0;
-        sc.s = 0;
-        if (ln == 0) sc = lq::make_scale(Q, V);
-        sc.R = __shfl_sync(0xffffffffu, sc.R, 0);
-        sc.s = __shfl_sync(0xffffffffu, sc.s, 0);
+        sc.s = Q >= (1ull << 28) ? 63 - __clzll((long long)Q) : 0;
+        uint64_t w = 1, xr = 0;
+        if (dec_mode) {
+            const int64_t low = (int64_t)dec_ld(par, 0), high = (int64_t)dec_ld(par, 1), value = (int64_t)dec_ld(par, 2);
+            w = (uint64_t)(high - low + 1);
+            xr = (uint64_t)(value - low);
+        }
+        uint64_t dhi = 0, dlo = 0, dden = 1;
+        if (ln == 0 && Q >= (1ull << 28)) {
+            dlo = ((1ull << 32) - (uint64_t)V) << 31;
+            dden = (sc.s >= 31 ? (Q >> (sc.s - 31)) : (Q << (31 - sc.s))) + 1;
+        } else if (ln == 1) {
+            dhi = xr >> 32;
+            dlo = xr << 32;
+            dden = w;
+        }
+        const uint32_t quo = lq::div_q32(dhi, dlo, dden);
+        sc.R = __shfl_sync(0xffffffffu, quo, 0);
+        const uint32_t target = __shfl_sync(0xffffffffu, quo, 1);
         if (dec_mode) {
             // lane w tests the start of local warp w; the owner is the last non-empty segment of the whole row
-            // whose start is at or below the value, so this CTA owns it unless the next CTA's start qualifies too
-            const int64_t low = (int64_t)dec_ld(par, 0), high = (int64_t)dec_ld(par, 1), value = (int64_t)dec_ld(par, 2);
-            const uint64_t w = (uint64_t)(high - low + 1), xr = (uint64_t)(value - low);
+            // whose start is at or below the probe, so this CTA owns it unless the next CTA's start qualifies too
             const int gw = (int)Clu<CL>::rank() * kWarps + ln;
             const int gb = seg_begin(gw, V), ge = seg_begin(gw + 1, V);
-            const bool ok = gb < ge && coder::scale32_ceil(lq::cum_of(exc, (uint32_t)(gb * VEC), sc), w) <= xr;
+            const bool ok = gb < ge && lq::cum_of(exc, (uint32_t)(gb * VEC), sc) <= target;
             const unsigned ball = __ballot_sync(0xffffffffu, ok);
             int owner = ball ? 31 - __clz((int)ball) : -1;
             if (CL > 1 && Clu<CL>::rank() + 1 < CL) {
                 const int nb = seg_begin(((int)Clu<CL>::rank() + 1) * kWarps, V);  // first group of the next CTA
                 const uint64_t nexc = base + __shfl_sync(0xffffffffu, inc, 31);
-                if (nb < groups(V) && coder::scale32_ceil(lq::cum_of(nexc, (uint32_t)(nb * VEC), sc), w) <= xr) owner = -1;
+                if (nb < groups(V) && lq::cum_of(nexc, (uint32_t)(nb * VEC), sc) <= target) owner = -1;
             }
-            if (ln == 0) g_ctl.owner = owner;
+            if (ln == 0) {
+                g_ctl.owner = owner;
+                g_ctl.target = target;
+            }
         }
         __syncwarp();
         if (ln == 0) {
@@ -658,10 +678,9 @@ build_kernel(const __grid_constant__ RowParams rp, int V, uint32_t* __restrict__
 }
 
 // ------------------------------------------------------------------ DECODE
-// val_to_symbol (arith_code.py:94-101) on the total d = 2^32 picks the last symbol whose lowest
-// coder offset ceil(cum * w / 2^32) (symbol_to_range's l, arith_code.py:110-111) is <= x = value - l.
-// Comparing through the multiplication keeps 128-bit divisions off the per-token serial path.
-__device__ __forceinline__ bool cum_le(uint32_t cum, uint64_t x, uint64_t w) { return coder::scale32_ceil(cum, w) <= x; }
+// val_to_symbol (arith_code.py:94-101) on the total d = 2^32: bisect_right(dist, target) with
+// target = ((value - l) * 2^32) // w, i.e. the last symbol whose exclusive cumulative is <= target.  The probe is
+// computed once per row in finish_row; every boundary test is then a 96-bit multiply-shift and a compare.
 
 // 8 stream bytes at byte offset b as a big-endian word, zeros past the end
 __device__ __forceinline__ uint64_t load_be64(const uint8_t* data, uint64_t nbytes, uint64_t b) {
@@ -716,59 +735,85 @@ decode_kernel(const __grid_constant__ RowParams rp, int V, lac_dec_state* __rest
         if (warp == ctl.owner) {
             const int64_t low = (int64_t)Eng::dec_ld(cur, 0), high = (int64_t)Eng::dec_ld(cur, 1);
             const int64_t value = (int64_t)Eng::dec_ld(cur, 2);
-            const uint64_t w = (uint64_t)(high - low + 1);
-            const uint64_t xr = (uint64_t)(value - low);
+            const uint32_t target = ctl.target;
             const lq::Scale sc = Eng::scale();
             const uint64_t Cb = ctl.pref[warp];
-            // ---- owner warp, three levels: slab (32 groups = 128 elements), lane, element.
-            // cum is monotone in index order, so at every level the owner is the LAST boundary at or below
-            // the value.  Slab totals come from REDUX (independent, pipelined); only the chosen slab is scanned.
-            uint32_t gs[IT];
+            // ---- owner warp.  Registers hold the segment slab-major (word j of lane l = element
+            // (32 k + l) VEC + e); the search wants it lane-major (lane l = 32 consecutive elements) so that ONE
+            // warp scan of lane totals plus ONE ballot finds the lane and everything after that is independent
+            // work inside that lane.  The 1024 words go through a padded scratch (address i + i / 32: conflict-
+            // free for both the slab-major writes and the lane-major reads).
+            uint32_t r[kPerThread];
+            if (VEC == 4) {  // 16-byte units: group i = 32 k + l goes to slot i + i / 8, lane l reads slots 9 l + p
+                uint4* xp = reinterpret_cast<uint4*>(ctl.xpose);
 #pragma unroll
-            for (int k = 0; k < IT; k++) {
-                uint32_t a = 0;  // VEC q values < 2^29.5 each: no overflow
-#pragma unroll
-                for (int e = 0; e < VEC; e++) a += q[k * VEC + e];
-                gs[k] = a;
-            }
-            uint64_t base = Cb, Csel = Cb;
-            int ksel = 0;
-#pragma unroll
-            for (int k = 0; k < IT; k++) {
-                const int g0 = gbeg + k * 32;
-                if (g0 < gend && cum_le(lq::cum_of(base, (uint32_t)(g0 * VEC), sc), xr, w)) {
-                    ksel = k;
-                    Csel = base;
+                for (int k = 0; k < IT; k++) {
+                    const int i = 32 * k + lane;
+                    xp[i + (i >> 3)] = make_uint4(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
                 }
-                base += warp_sum48((uint64_t)gs[k]);
-            }
-            uint32_t gsel = 0, qe[VEC];
+                __syncwarp();
 #pragma unroll
-            for (int e = 0; e < VEC; e++) qe[e] = 0;
-#pragma unroll
-            for (int k = 0; k < IT; k++) {
-                if (k == ksel) {  // warp-uniform
-                    gsel = gs[k];
-#pragma unroll
-                    for (int e = 0; e < VEC; e++) qe[e] = q[k * VEC + e];
+                for (int p = 0; p < kPerThread / 4; p++) {
+                    const uint4 v = xp[9 * lane + p];
+                    r[4 * p] = v.x;
+                    r[4 * p + 1] = v.y;
+                    r[4 * p + 2] = v.z;
+                    r[4 * p + 3] = v.w;
                 }
+            } else {  // 4-byte units: element i = 32 k + l goes to word i + i / 32, lane l reads words 33 l + j
+                uint32_t* xp = ctl.xpose;
+#pragma unroll
+                for (int k = 0; k < IT; k++) {
+                    const int i = 32 * k + lane;
+                    xp[i + (i >> 5)] = q[k];
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < kPerThread; j++) r[j] = xp[33 * lane + j];
             }
-            const uint64_t inc = warp_incl_scan((uint64_t)gsel, lane);
-            const uint64_t C = Csel + inc - gsel;
-            const int gl = gbeg + ksel * 32 + lane;
-            const bool ok = gl < gend && cum_le(lq::cum_of(C, (uint32_t)(gl * VEC), sc), xr, w);
+            uint32_t s4[kPerThread / 4];  // sums of 4 consecutive elements (< 2^31.5)
+            uint64_t L = 0;
+#pragma unroll
+            for (int p = 0; p < kPerThread / 4; p++) {
+                s4[p] = (r[4 * p] + r[4 * p + 1]) + (r[4 * p + 2] + r[4 * p + 3]);
+                L += s4[p];
+            }
+            const int e0 = gbeg * VEC + 32 * lane, eend = gend * VEC;  // this lane's first element / end of segment
+            const uint64_t inc = warp_incl_scan(L, lane);
+            const uint64_t Cl = Cb + inc - L;
+            const bool ok = e0 < eend && lq::cum_of(Cl, (uint32_t)e0, sc) <= target;
             const unsigned ball = __ballot_sync(0xffffffffu, ok);
             if (lane == 31 - __clz((int)ball)) {
-                // ---- element level (one lane)
-                const int g = gl;
-                int sym = g * VEC;
-                uint64_t Cs = C, Ce = C;
+                // ---- inside the lane: last group of 4 whose start qualifies, then last element of that group
+                uint64_t Cp = Cl, Cg = Cl;
+                int psel = 0;
+#pragma unroll
+                for (int p = 1; p < kPerThread / 4; p++) {
+                    Cp += s4[p - 1];
+                    if (e0 + 4 * p < eend && lq::cum_of(Cp, (uint32_t)(e0 + 4 * p), sc) <= target) {
+                        psel = p;
+                        Cg = Cp;
+                    }
+                }
+                uint32_t qe[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) qe[e] = 0;
+#pragma unroll
+                for (int p = 0; p < kPerThread / 4; p++) {
+                    if (p == psel) {
+#pragma unroll
+                        for (int e = 0; e < 4; e++) qe[e] = r[4 * p + e];
+                    }
+                }
+                const int eg = e0 + 4 * psel;
+                int sym = eg;
+                uint64_t Cs = Cg, Ce = Cg;
                 uint32_t qsym = qe[0];
 #pragma unroll
-                for (int e = 1; e < VEC; e++) {
+                for (int e = 1; e < 4; e++) {
                     Ce += qe[e - 1];
-                    if (cum_le(lq::cum_of(Ce, (uint32_t)(g * VEC + e), sc), xr, w)) {
-                        sym = g * VEC + e;
+                    if (eg + e < eend && lq::cum_of(Ce, (uint32_t)(eg + e), sc) <= target) {
+                        sym = eg + e;
                         Cs = Ce;
                         qsym = qe[e];
                     }

@@ -60,6 +60,20 @@ struct Scale {
     int s;
 };
 
+// floor(((hi << 64) | lo) / den) for a quotient known to fit 32 bits (den < 2^62): fp64 estimate, off by at
+// most one, then an exact fix-up.  Branch-free, so different lanes can divide different operands together.
+__device__ __forceinline__ uint32_t div_q32(uint64_t hi, uint64_t lo, uint64_t den) {
+    const double num = __fma_rn((double)hi, 18446744073709551616.0, (double)lo);
+    uint64_t q = (uint64_t)__ddiv_rz(num, (double)den);
+    // remainder r = num - q * den as a signed 128-bit value, via 64-bit halves
+    const uint64_t plo = q * den, phi = __umul64hi(q, den);
+    const uint64_t rlo = lo - plo;
+    const int64_t rhi = (int64_t)(hi - phi - (lo < plo ? 1u : 0u));
+    const bool neg = rhi < 0;
+    const bool big = !neg && (rhi > 0 || rlo >= den);
+    return (uint32_t)(q - (neg ? 1u : 0u) + (big ? 1u : 0u));
+}
+
 __device__ __forceinline__ Scale make_scale(uint64_t Q, int V) {
     Scale k;
     k.Q = Q;
@@ -69,13 +83,7 @@ __device__ __forceinline__ Scale make_scale(uint64_t Q, int V) {
         k.s = 63 - __clzll((long long)Q);  // >= 28: the row maximum contributes q >= 2^28.5
         const uint64_t N = ((1ull << 32) - (uint64_t)V) << 31;
         const uint64_t D = (k.s >= 31 ? (Q >> (k.s - 31)) : (Q << (31 - k.s))) + 1;  // (2^31, 2^32]
-        // R = floor(N / D) <= M * 2^s / Q.  fp64 estimate (off by at most 1) + exact fix-up:
-        // far shorter dependent chain than the generic 64-bit division.
-        uint64_t r = (uint64_t)__ddiv_rz((double)N, (double)D);
-        int64_t rem = (int64_t)(N - r * D);
-        if (rem < 0) r -= 1;
-        else if (rem >= (int64_t)D) r += 1;
-        k.R = (uint32_t)r;
+        k.R = div_q32(0, N, D);  // R = floor(N / D) <= M * 2^s / Q
     }
     return k;
 }
