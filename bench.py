@@ -54,6 +54,15 @@ def workload_config(n_gpus):
     }
 
 
+def measured_traffic(kernel, vocab, rows):
+    """DRAM bytes per launch from the committed ncu capture, if it is for this exact workload; else None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1", "traffic.json")))[kernel]
+        return t["dram_bytes"] if (t["vocab"], t["rows"]) == (vocab, rows) else None
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -299,7 +308,7 @@ def run_gpu(args):
             "vs_baseline": None, "dtype": "f32->u32/u64", "data": "synthetic", "config": workload_config(world),
             "roofline": {"bound": "hbm", "kernel": "lookup_kernel (fused softmax -> fixed-total quantisation -> clamp -> prefix sums -> (lo, hi) of the coded symbol)",
                          "achieved": look_gbs, "peak": peak, "unit": "GB/s", "frac": look_gbs / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "traffic": measured_traffic("lookup_kernel", V, rows), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "ms_per_launch": lookup_ms,
                          "decode_kernel": {"achieved": dec_gbs, "frac": dec_gbs / peak, "ms_per_launch": decode_ms},
                          "coder_kernel_ms": coder_ms},
