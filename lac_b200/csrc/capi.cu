@@ -102,6 +102,7 @@ int lac_cdf_lookup_f32(const float* d_logits, int64_t rows, int32_t vocab, int64
     if (!d_logits || !d_syms || !d_pairs || rows < 0 || row_stride < vocab)
         return fail(LAC_E_ARG, "lac_cdf_lookup_f32: bad argument");
     if (int rc = check_vocab(vocab, d_logits, row_stride)) return rc;
+    if ((uintptr_t)d_pairs & 7) return fail(LAC_E_ARG, "lac_cdf_lookup_f32: d_pairs must be 8-byte aligned");
     CK(lac::launch_lookup(d_logits, rows, vocab, row_stride, d_syms, d_pairs, d_status, (cudaStream_t)stream),
        "lac_cdf_lookup_f32");
     return LAC_OK;

@@ -683,11 +683,21 @@ build_kernel(const __grid_constant__ RowParams rp, int V, uint32_t* __restrict__
 // computed once per row in finish_row; every boundary test is then a 96-bit multiply-shift and a compare.
 
 // 8 stream bytes at byte offset b as a big-endian word, zeros past the end
+// Assembled as two 32-bit halves from unconditional loads at clamped addresses plus a mask.  (The obvious
+// form -- a 64-bit accumulator fed by predicated byte loads -- was observed to be miscompiled by ptxas 12.9 in
+// one instantiation: a CS2R-zeroed register pair was read 5 cycles later still holding its previous content,
+// which corrupted the window of streams shorter than 22 bytes.  tests/test_gpu_parity.py pins that case.)
 __device__ __forceinline__ uint64_t load_be64(const uint8_t* data, uint64_t nbytes, uint64_t b) {
-    uint64_t v = 0;
+    if (b >= nbytes) return 0;
+    uint32_t w[2] = {0u, 0u};
 #pragma unroll
-    for (int i = 0; i < 8; i++) v = (v << 8) | (uint64_t)((b + i) < nbytes ? data[b + i] : 0);
-    return v;
+    for (int i = 0; i < 8; i++) {
+        const uint64_t idx = b + i;
+        const bool in = idx < nbytes;
+        const uint32_t byte = (uint32_t)data[in ? idx : b] & (in ? 0xFFu : 0u);
+        w[i >> 2] = (w[i >> 2] << 8) | byte;
+    }
+    return ((uint64_t)w[0] << 32) | w[1];
 }
 
 __device__ __forceinline__ void dec_load_state(DecShared& d, const lac_dec_state* st, const uint8_t* bytes,

@@ -61,3 +61,19 @@ def test_product_never_touches_the_oracle():
                 code = "\n".join(l for l in src.splitlines() if not l.lstrip().startswith(("#", "//", "*", "/*")))
                 assert "import oracle" not in code and "from oracle" not in code, f
                 assert "liblac_oracle" not in code, f
+
+
+def test_built_library_has_no_short_cs2r_consumers():
+    """tools/sass_hazard_scan.py: the SASS pattern that once corrupted the decoder's bit window must not
+    reappear in a rebuild (needs cuobjdump; skipped where the CUDA toolkit is absent)."""
+    import shutil
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    so = root / "lac_b200" / "_lib" / "liblac_b200.so"
+    if shutil.which("cuobjdump") is None or not so.exists():
+        pytest.skip("cuobjdump or the built library is not available")
+    r = subprocess.run([sys.executable, str(root / "tools" / "sass_hazard_scan.py"), str(so)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]

@@ -96,6 +96,23 @@ def test_cluster_encode_decode_roundtrip(V, S, T):
     assert np.array_equal(step, syms)
 
 
+@pytest.mark.parametrize("V,S", [(32000, 60), (65536, 40), (131072, 24)])
+def test_streams_ending_inside_the_first_bit_window(V, S):
+    """Streams of 15..22 bytes end inside the 16 bytes the decoder loads at stream start: the bytes past the end
+    must read as zeros (A_from_bin pads with zeros, arith_code.py:262-266) and the in-range bytes next to them
+    must not be disturbed.  (Regression: a predicated byte gather was once miscompiled for exactly this case.)"""
+    for T, scale in ((5, 6.0), (5, 8.0), (6, 4.0)):
+        rng = np.random.default_rng(V + T)
+        logits = (rng.standard_normal((S, T, V)) * scale).astype(np.float32)
+        syms = rng.integers(0, V, (S, T)).astype(np.int32)
+        dl = _dev(logits)
+        enc = coder.StreamEncoder(S, capacity_bytes=T * 8 + 64)
+        enc.encode_logits(dl, _dev(syms), finish=True)
+        streams, _ = enc.bitstreams()
+        assert any(15 <= len(b) <= 22 for b in streams)
+        assert np.array_equal(coder.StreamDecoder(streams).decode_logits(dl).cpu().numpy(), syms)
+
+
 def test_wide_unaligned_vocab_is_rejected():
     with pytest.raises(_ffi.LacError):
         coder.cdf_build(torch.zeros((2, 40001), dtype=torch.float32, device="cuda"))
