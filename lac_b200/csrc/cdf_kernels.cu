@@ -1,5 +1,5 @@
-// cdf_kernels.cu -- fused logits -> LQ32 CDF kernels (north-star part (a)) and the fused
-// decode step (part (b), decoder side).
+// cdf_kernels.cu -- fused logits -> LQ32 CDF kernels (north-star part (a)) and the decoder side of
+// part (b): a bandwidth-bound row-summary pass plus a latency-bound serial pass per stream.
 //
 // One persistent CTA of 1024 threads per SM walks its rows.  Warp w owns a contiguous
 // segment of the row; the row is read from HBM exactly once and then lives in registers:
@@ -17,8 +17,10 @@
 //                    cum[sym], cum[sym+1] from masked integer sums (no table is written); the other
 //                    31 warps are already draining the next row.
 //            BUILD : whole table via in-warp exclusive scans.
-//            DECODE: 8 interleaved lane scans + ballots locate the 4-element group in the owner warp,
-//                    one lane finishes the search and runs the A_from_bin state update.
+//            SUMMARY (decode, pass 1): the finishing warp writes the row's reference, scale and the 32 * CL
+//                    warp-segment prefixes (272 bytes per 32000-element row); nobody waits for anything.
+//            DECODE  (pass 2, decode_serial_kernel): one warp per stream walks its tokens: probe -> segment
+//                    from the summary -> re-read that one segment (<= 4 KB) -> q -> symbol -> A_from_bin update.
 // The integer formulation (lq32.cuh) makes the result independent of this decomposition.
 #include <climits>
 #include <cstdint>
@@ -33,6 +35,7 @@ namespace lac {
 constexpr int kThreads = 1024;
 constexpr int kWarps = kThreads / 32;
 constexpr int kPerThread = 32;  // row elements held per thread
+constexpr int kSummHdr = 2;     // row summary (decode pass 1): 2 header words, then 32 * CL prefixes (all uint64)
 
 // TMA chunks per row.  Measured on B200 (profiles/microbench/tma_stream.cu): every cp.async.bulk costs
 // ~0.2 us of per-SM TMA time regardless of size, so 8 x 16 KB chunks cap at 4.7 TB/s while 2 x 64 KB
@@ -211,16 +214,6 @@ struct Clu {
 
 // ------------------------------------------------------------------ shared control block
 constexpr int kMaxCluster = 8;
-struct DecShared {
-    int64_t low, high, value;
-    uint64_t pos;             // next bit of the stream
-    uint64_t win_hi, win_lo;  // 16 stream bytes starting at byte win_byte, big-endian
-    uint64_t win_byte;
-    int64_t data_off;
-    uint64_t nbytes;
-};
-constexpr int kDecWords = sizeof(DecShared) / 8;
-
 struct Ctl {
     uint64_t full[kMaxChunks];  // TMA chunk landed
     uint64_t done;              // row-level bookkeeping published (phase = row parity)
@@ -234,11 +227,7 @@ struct Ctl {
     uint64_t Q;                 // row total                               } warp to finish phase B, then
     uint32_t R;                 // lq::Scale                               } `done` flips
     int s;                      //                                         }
-    int owner;                  // decode: local warp whose segment holds the symbol, or -1
-    uint32_t target;            // decode: floor(((value - low) << 32) / (high - low + 1)), val_to_symbol's probe
     uint32_t arrive;            // warps done with phase B of the current row
-    DecShared dec[2];           // decoder state (rank 0's copy is the live one), double-buffered by row parity
-    __align__(16) uint32_t xpose[kWarps * 32 + 4 * 32];  // decode owner warp: q values on their way to lane-major order (padded)
 };
 
 // Rows visited by this CTA / cluster, in order: outer index s = first, += stride; inner t < Ts.
@@ -246,14 +235,20 @@ struct Ctl {
 struct RowParams {
     const float* base;
     int64_t n_outer, T, so, st;
-    const int32_t* ntok;
+    const int32_t* ntok;  // per outer index: tokens present (nullptr: T everywhere)
+    int64_t t0;           // ntok counts from t0 tokens before `base` (token-chunked decode), so ntok[s] - t0 remain
 };
+__device__ __forceinline__ int tokens_of(const RowParams& p, int64_t s) {
+    if (!p.ntok) return (int)p.T;
+    const int64_t n = (int64_t)p.ntok[s] - p.t0;
+    return (int)(n < 0 ? 0 : (n > p.T ? p.T : n));
+}
 struct RowSeq {
     int64_t s;
     int t, Ts;
     __device__ __forceinline__ void skip_empty(const RowParams& p, uint32_t stride) {
         while (s < p.n_outer) {
-            Ts = p.ntok ? p.ntok[s] : (int)p.T;
+            Ts = tokens_of(p, s);
             if (Ts > 0) break;
             s += stride;
         }
@@ -272,6 +267,37 @@ struct RowSeq {
             t = 0;
             skip_empty(p, stride);
         }
+    }
+};
+// All rows (s, t) of the launch dealt round-robin to the CTAs / clusters regardless of the stream they belong to
+// (flat index s * T + t = first + i * stride), rows past a stream's token count skipped.  No division per row.
+struct FlatSeq {
+    int64_t s, ds;
+    int t, dt;
+    __device__ __forceinline__ void skip_absent(const RowParams& p) {
+        while (s < p.n_outer && p.ntok && t >= tokens_of(p, s)) step(p);
+    }
+    __device__ __forceinline__ void step(const RowParams& p) {
+        s += ds;
+        t += dt;
+        if (t >= (int)p.T) {
+            t -= (int)p.T;
+            s++;
+        }
+    }
+    __device__ __forceinline__ void init(const RowParams& p, uint32_t first, uint32_t stride) {
+        s = first / p.T;
+        t = (int)(first % p.T);
+        ds = stride / p.T;
+        dt = (int)(stride % p.T);
+        skip_absent(p);
+    }
+    __device__ __forceinline__ bool valid(const RowParams& p) const { return s < p.n_outer; }
+    __device__ __forceinline__ const float* ptr(const RowParams& p) const { return p.base + s * p.so + t * p.st; }
+    __device__ __forceinline__ int64_t index(const RowParams& p) const { return s * p.T + t; }
+    __device__ __forceinline__ void next(const RowParams& p) {
+        step(p);
+        skip_absent(p);
     }
 };
 
@@ -337,9 +363,10 @@ struct RowEngine {
     // One row: stage it into registers, phase A (maximum), the row's single block barrier (plus, in a cluster,
     // the exchange of the CTA maxima), phase B (q, sums).  `next_row` (or nullptr) is prefetched as soon as this
     // row has left shared memory.  On return q[] holds this thread's q values; the row-level results
-    // (g_ctl.pref, Q, R, s, owner) are valid once wait_done() returns.  dec_mode: also find the decode owner.
+    // (g_ctl.pref, Q, R, s) are valid once wait_done() returns.  summ != nullptr: the finishing warp also writes
+    // the row summary (reference, scale, warp-segment prefixes) there.
     __device__ __forceinline__ void reduce(const float* __restrict__ row, const float* next_row, int V,
-                                           uint32_t (&q)[kPerThread], bool dec_mode = false, bool lazy = false) {
+                                           uint32_t (&q)[kPerThread], bool lazy = false, uint64_t* summ = nullptr) {
         float x[kPerThread];
         {
             const int gb = gbeg(V), ge = gend(V), ln = lane();
@@ -401,6 +428,7 @@ struct RowEngine {
         // i.e. q = 0 everywhere, without a second code path)
         const int nloc = lq::ref_of_max(ord2f(mx));
         const uint32_t nref_u = lq::ref_valid(nloc) ? (uint32_t)nloc : 0xFFFFFFFFu;
+        uint32_t nrow_u = nref_u;  // reference of the whole row (differs from nref_u only in a cluster)
         uint64_t lane_sum = 0;
         if (CL == 1) {
 #pragma unroll
@@ -420,6 +448,7 @@ struct RowEngine {
             const int nref = lq::ref_of_max(ord2f(mx));
             uint32_t delta = (uint32_t)nref - (uint32_t)nloc;
             delta = (lq::ref_valid(nref) && delta < 32u) ? delta : 32u;
+            nrow_u = lq::ref_valid(nref) ? (uint32_t)nref : 0xFFFFFFFFu;
 #pragma unroll
             for (int i = 0; i < kPerThread; i += 4) {
 #pragma unroll
@@ -435,26 +464,16 @@ struct RowEngine {
             prev = atomicAdd(&g_ctl.arrive, 1u);
         }
         prev = __shfl_sync(0xffffffffu, prev, 0);
-        if (prev == kWarps - 1) finish_row(V, par, dec_mode, lazy);  // last warp of the row: every wsum[] is visible
+        if (prev == kWarps - 1) finish_row(V, par, lazy, summ, nrow_u);  // last warp of the row: every wsum[] is visible
         it++;
-    }
-
-    // Decoder state lives in rank 0's shared memory (everyone reads / the owner lane writes it there).
-    static __device__ __forceinline__ uint64_t dec_ld(uint32_t buf, int word) {
-        const uint32_t a = smem_u32(reinterpret_cast<const uint64_t*>(&g_ctl.dec[buf]) + word);
-        if (CL == 1) return *(reinterpret_cast<const volatile uint64_t*>(&g_ctl.dec[buf]) + word);
-        return ld_cluster_u64(mapa(a, 0));
-    }
-    static __device__ __forceinline__ void dec_st(uint32_t buf, int word, uint64_t v) {
-        const uint32_t a = smem_u32(reinterpret_cast<const uint64_t*>(&g_ctl.dec[buf]) + word);
-        if (CL == 1) *(reinterpret_cast<volatile uint64_t*>(&g_ctl.dec[buf]) + word) = v;
-        else st_cluster_u64(mapa(a, 0), v);
     }
 
     // Row-level bookkeeping, run by exactly one warp per CTA per row.
     // lazy (lookup in a cluster): only publish this CTA's total and local prefixes; whoever needs the row-wide
     // numbers (the one owner warp) waits for the peers itself, so this warp is not held up.
-    static __device__ __noinline__ void finish_row(int V, uint32_t par, bool dec_mode, bool lazy) {
+    // summ (decode, pass 1): row summary = { nref | R << 32, s, prefix[32 * CL] }; lane l of every CTA writes the
+    // row-wide exclusive prefix at the start of its warp l, rank 0 writes the two header words.
+    static __device__ __noinline__ void finish_row(int V, uint32_t par, bool lazy, uint64_t* summ, uint32_t nrow_u) {
         const int ln = lane();
         fence_acq_rel_cta();
         const uint64_t v = *reinterpret_cast<volatile uint64_t*>(&g_ctl.wsum[ln]);
@@ -487,46 +506,12 @@ struct RowEngine {
         }
         const uint64_t exc = base + inc - v;  // row-wide exclusive prefix at the start of local warp `ln`
         g_ctl.pref[ln] = exc;
-        // The two divisions of the row run side by side: lane 0 the scale R = floor(N / D), lane 1 (decode) the
-        // probe of val_to_symbol, target = floor(((value - low) << 32) / w) (arith_code.py:94-101 with d = 2^32).
-        lq::Scale sc;
-        sc.Q = Q;
-        sc.R = 0;
-        sc.s = Q >= (1ull << 28) ? 63 - __clzll((long long)Q) : 0;
-        uint64_t w = 1, xr = 0;
-        if (dec_mode) {
-            const int64_t low = (int64_t)dec_ld(par, 0), high = (int64_t)dec_ld(par, 1), value = (int64_t)dec_ld(par, 2);
-            w = (uint64_t)(high - low + 1);
-            xr = (uint64_t)(value - low);
-        }
-        uint64_t dhi = 0, dlo = 0, dden = 1;
-        if (ln == 0 && Q >= (1ull << 28)) {
-            dlo = ((1ull << 32) - (uint64_t)V) << 31;
-            dden = (sc.s >= 31 ? (Q >> (sc.s - 31)) : (Q << (31 - sc.s))) + 1;
-        } else if (ln == 1) {
-            dhi = xr >> 32;
-            dlo = xr << 32;
-            dden = w;
-        }
-        const uint32_t quo = lq::div_q32(dhi, dlo, dden);
-        sc.R = __shfl_sync(0xffffffffu, quo, 0);
-        const uint32_t target = __shfl_sync(0xffffffffu, quo, 1);
-        if (dec_mode) {
-            // lane w tests the start of local warp w; the owner is the last non-empty segment of the whole row
-            // whose start is at or below the probe, so this CTA owns it unless the next CTA's start qualifies too
-            const int gw = (int)Clu<CL>::rank() * kWarps + ln;
-            const int gb = seg_begin(gw, V), ge = seg_begin(gw + 1, V);
-            const bool ok = gb < ge && lq::cum_of(exc, (uint32_t)(gb * VEC), sc) <= target;
-            const unsigned ball = __ballot_sync(0xffffffffu, ok);
-            int owner = ball ? 31 - __clz((int)ball) : -1;
-            if (CL > 1 && Clu<CL>::rank() + 1 < CL) {
-                const int nb = seg_begin(((int)Clu<CL>::rank() + 1) * kWarps, V);  // first group of the next CTA
-                const uint64_t nexc = base + __shfl_sync(0xffffffffu, inc, 31);
-                if (nb < groups(V) && lq::cum_of(nexc, (uint32_t)(nb * VEC), sc) <= target) owner = -1;
-            }
-            if (ln == 0) {
-                g_ctl.owner = owner;
-                g_ctl.target = target;
+        const lq::Scale sc = lq::make_scale(Q, V);  // one division, the same in every lane
+        if (summ) {
+            summ[kSummHdr + (int)Clu<CL>::rank() * kWarps + ln] = exc;
+            if (ln == 0 && Clu<CL>::rank() == 0) {
+                summ[0] = (uint64_t)nrow_u | ((uint64_t)sc.R << 32);
+                summ[1] = (uint64_t)(uint32_t)sc.s;
             }
         }
         __syncwarp();
@@ -583,7 +568,7 @@ lookup_kernel(const __grid_constant__ RowParams rp, int V, const int32_t* __rest
         const int sym = __ldg(syms + r);  // issued now, consumed after the row's compute phases
         seq.next(rp, stride);
         uint32_t q[kPerThread];
-        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, V, q, false, CL > 1);
+        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, V, q, CL > 1);
         const int warp = Eng::warp(), lane = Eng::lane(), gbeg = Eng::gbeg(V), gend = Eng::gend(V);
         if (sym < 0 || sym >= V) {
             if (threadIdx.x == 0 && Clu<CL>::rank() == 0) {
@@ -700,180 +685,183 @@ __device__ __forceinline__ uint64_t load_be64(const uint8_t* data, uint64_t nbyt
     return ((uint64_t)w[0] << 32) | w[1];
 }
 
-__device__ __forceinline__ void dec_load_state(DecShared& d, const lac_dec_state* st, const uint8_t* bytes,
-                                               const int64_t* offsets, int64_t s) {
-    d.low = st[s].low;
-    d.high = st[s].high;
-    d.value = st[s].value;
-    d.pos = st[s].pos;
-    d.data_off = offsets[s];
-    d.nbytes = (uint64_t)(offsets[s + 1] - offsets[s]);
-    d.win_byte = d.pos >> 3;
-    d.win_hi = load_be64(bytes + d.data_off, d.nbytes, d.win_byte);
-    d.win_lo = load_be64(bytes + d.data_off, d.nbytes, d.win_byte + 8);
-}
-
+// ---- pass 1: row summaries.  The same engine as LOOKUP without an owner: rows are dealt to the CTAs / clusters
+// regardless of their stream (a 4-stream job still fills the machine), and the only output is the summary the
+// finishing warp writes -- 16 + 256 * CL bytes per row next to the 4 * V bytes read.
 template <int VEC, bool TMA, int NCH, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
-decode_kernel(const __grid_constant__ RowParams rp, int V, lac_dec_state* __restrict__ state,
-              const uint8_t* __restrict__ bytes, const int64_t* __restrict__ offsets,
-              int32_t* __restrict__ syms, int64_t sym_stride, int P) {
+summary_kernel(const __grid_constant__ RowParams rp, int V, uint64_t* __restrict__ summ) {
     using Eng = RowEngine<VEC, TMA, NCH, CL>;
-    Ctl& ctl = g_ctl;
     Eng eng;
     eng.setup();
-    constexpr int IT = kPerThread / VEC;
-    const uint32_t stride = Clu<CL>::count();
-    RowSeq seq;
-    seq.init(rp, Clu<CL>::id(), stride);
+    FlatSeq seq;
+    seq.init(rp, Clu<CL>::id(), Clu<CL>::count());
     if (seq.valid(rp)) Eng::issue(seq.ptr(rp), V);
     while (seq.valid(rp)) {
-        const int64_t s = seq.s;
-        const int t = seq.t;
-        const bool first = (t == 0), last = (t == seq.Ts - 1);
+        uint64_t* out = summ + seq.index(rp) * (kSummHdr + CL * kWarps);
         const float* row = seq.ptr(rp);
-        seq.next(rp, stride);
-        // The decoder state of row `it` sits in dec[it & 1] of rank 0; the owner lane of this row writes the
-        // state of the next row into dec[(it + 1) & 1].  A new stream's state is loaded before the row's block
-        // barrier; it reaches the other CTAs through the release / acquire chain of the totals exchange.
-        const uint32_t cur = eng.it & 1;
-        if (first && threadIdx.x == 0 && Clu<CL>::rank() == 0) dec_load_state(ctl.dec[cur], state, bytes, offsets, s);
+        seq.next(rp);
         uint32_t q[kPerThread];
-        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, V, q, true);
-        eng.wait_done();
-        const int warp = Eng::warp(), lane = Eng::lane(), gbeg = Eng::gbeg(V), gend = Eng::gend(V);
-        if (warp == ctl.owner) {
-            const int64_t low = (int64_t)Eng::dec_ld(cur, 0), high = (int64_t)Eng::dec_ld(cur, 1);
-            const int64_t value = (int64_t)Eng::dec_ld(cur, 2);
-            const uint32_t target = ctl.target;
-            const lq::Scale sc = Eng::scale();
-            const uint64_t Cb = ctl.pref[warp];
-            // ---- owner warp.  Registers hold the segment slab-major (word j of lane l = element
-            // (32 k + l) VEC + e); the search wants it lane-major (lane l = 32 consecutive elements) so that ONE
-            // warp scan of lane totals plus ONE ballot finds the lane and everything after that is independent
-            // work inside that lane.  The 1024 words go through a padded scratch (address i + i / 32: conflict-
-            // free for both the slab-major writes and the lane-major reads).
-            uint32_t r[kPerThread];
-            if (VEC == 4) {  // 16-byte units: group i = 32 k + l goes to slot i + i / 8, lane l reads slots 9 l + p
-                uint4* xp = reinterpret_cast<uint4*>(ctl.xpose);
-#pragma unroll
-                for (int k = 0; k < IT; k++) {
-                    const int i = 32 * k + lane;
-                    xp[i + (i >> 3)] = make_uint4(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
-                }
-                __syncwarp();
-#pragma unroll
-                for (int p = 0; p < kPerThread / 4; p++) {
-                    const uint4 v = xp[9 * lane + p];
-                    r[4 * p] = v.x;
-                    r[4 * p + 1] = v.y;
-                    r[4 * p + 2] = v.z;
-                    r[4 * p + 3] = v.w;
-                }
-            } else {  // 4-byte units: element i = 32 k + l goes to word i + i / 32, lane l reads words 33 l + j
-                uint32_t* xp = ctl.xpose;
-#pragma unroll
-                for (int k = 0; k < IT; k++) {
-                    const int i = 32 * k + lane;
-                    xp[i + (i >> 5)] = q[k];
-                }
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < kPerThread; j++) r[j] = xp[33 * lane + j];
-            }
-            uint32_t s4[kPerThread / 4];  // sums of 4 consecutive elements (< 2^31.5)
-            uint64_t L = 0;
-#pragma unroll
-            for (int p = 0; p < kPerThread / 4; p++) {
-                s4[p] = (r[4 * p] + r[4 * p + 1]) + (r[4 * p + 2] + r[4 * p + 3]);
-                L += s4[p];
-            }
-            const int e0 = gbeg * VEC + 32 * lane, eend = gend * VEC;  // this lane's first element / end of segment
-            const uint64_t inc = warp_incl_scan(L, lane);
-            const uint64_t Cl = Cb + inc - L;
-            const bool ok = e0 < eend && lq::cum_of(Cl, (uint32_t)e0, sc) <= target;
-            const unsigned ball = __ballot_sync(0xffffffffu, ok);
-            if (lane == 31 - __clz((int)ball)) {
-                // ---- inside the lane: last group of 4 whose start qualifies, then last element of that group
-                uint64_t Cp = Cl, Cg = Cl;
-                int psel = 0;
-#pragma unroll
-                for (int p = 1; p < kPerThread / 4; p++) {
-                    Cp += s4[p - 1];
-                    if (e0 + 4 * p < eend && lq::cum_of(Cp, (uint32_t)(e0 + 4 * p), sc) <= target) {
-                        psel = p;
-                        Cg = Cp;
-                    }
-                }
-                uint32_t qe[4];
-#pragma unroll
-                for (int e = 0; e < 4; e++) qe[e] = 0;
-#pragma unroll
-                for (int p = 0; p < kPerThread / 4; p++) {
-                    if (p == psel) {
-#pragma unroll
-                        for (int e = 0; e < 4; e++) qe[e] = r[4 * p + e];
-                    }
-                }
-                const int eg = e0 + 4 * psel;
-                int sym = eg;
-                uint64_t Cs = Cg, Ce = Cg;
-                uint32_t qsym = qe[0];
-#pragma unroll
-                for (int e = 1; e < 4; e++) {
-                    Ce += qe[e - 1];
-                    if (eg + e < eend && lq::cum_of(Ce, (uint32_t)(eg + e), sc) <= target) {
-                        sym = eg + e;
-                        Cs = Ce;
-                        qsym = qe[e];
-                    }
-                }
-                const uint32_t lo = lq::cum_of(Cs, (uint32_t)sym, sc);
-                const uint32_t hi = (sym == V - 1) ? 0u : lq::cum_of(Cs + qsym, (uint32_t)sym + 1, sc);
-                // ---- A_from_bin.emit_symbol + emit_bit loop (arith_code.py:278-298)
-                int64_t nl = low, nh = high;
-                coder::ac_narrow32(nl, nh, lo, hi);
-                const int64_t off = value - nl;  // the value stays inside [nl, nh]
-                const int k = coder::renorm_count((uint64_t)(nh - nl + 1), P);
-                coder::renorm_apply(nl, nh, P, k);
-                // next k bits from the 128-bit window (k <= 60, window offset < 64)
-                const uint64_t pos = Eng::dec_ld(cur, 3);
-                const uint64_t hi64 = Eng::dec_ld(cur, 4), lo64 = Eng::dec_ld(cur, 5), wb = Eng::dec_ld(cur, 6);
-                const int o = (int)(pos - (wb << 3));
-                const uint64_t comb = o ? ((hi64 << o) | (lo64 >> (64 - o))) : hi64;
-                const uint64_t nb = k ? (comb >> (64 - k)) : 0;
-                const int64_t nv = nl + (off << k) + (int64_t)nb;
-                syms[s * sym_stride + t] = sym;
-                if (last) {
-                    state[s].low = nl;
-                    state[s].high = nh;
-                    state[s].value = nv;
-                    state[s].pos = pos + (uint64_t)k;
-                } else {
-                    const uint32_t nxt = cur ^ 1;
-                    const int64_t data_off = (int64_t)Eng::dec_ld(cur, 7);
-                    const uint64_t nbytes = Eng::dec_ld(cur, 8);
-                    Eng::dec_st(nxt, 0, (uint64_t)nl);
-                    Eng::dec_st(nxt, 1, (uint64_t)nh);
-                    Eng::dec_st(nxt, 2, (uint64_t)nv);
-                    Eng::dec_st(nxt, 3, pos + (uint64_t)k);
-                    if (o + k >= 64) {  // slide the window by 8 bytes
-                        Eng::dec_st(nxt, 4, lo64);
-                        Eng::dec_st(nxt, 5, load_be64(bytes + data_off, nbytes, wb + 16));
-                        Eng::dec_st(nxt, 6, wb + 8);
-                    } else {
-                        Eng::dec_st(nxt, 4, hi64);
-                        Eng::dec_st(nxt, 5, lo64);
-                        Eng::dec_st(nxt, 6, wb);
-                    }
-                    Eng::dec_st(nxt, 7, (uint64_t)data_off);
-                    Eng::dec_st(nxt, 8, nbytes);
-                }
-            }
-            __syncwarp();
-        }
+        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, V, q, false, out);
     }
     Eng::teardown();
+}
+
+// ---- pass 2: the serial part.  One warp per stream; every lane carries the same A_from_bin state
+// (arith_code.py:233-306) in registers.  Per token:
+//   probe    target = floor(((value - low) << 32) / w)                        (val_to_symbol, arith_code.py:94-101)
+//   level 1  the last non-empty warp segment of the row whose first cumulative is <= target (summary prefixes)
+//   level 2  that segment (<= 1024 elements, <= 4 KB) is read again, lane-major (lane l = 32 consecutive elements),
+//            q recomputed against the row reference (bit-identical to pass 1 by construction of LQ32), one warp scan
+//            + ballot picks the lane, the rest of the search is independent work inside each lane
+//   update   narrow, renormalise by k bits at once, pull k bits from a 24-byte register window of the stream
+// The logits segment comes from HBM (pass 1 streamed the rows with evict-first), ~3 % extra traffic.
+template <int VEC>
+__global__ void __launch_bounds__(128)
+decode_serial_kernel(const __grid_constant__ RowParams rp, int V, int cl_log2, const uint64_t* __restrict__ summ,
+                     lac_dec_state* __restrict__ state, const uint8_t* __restrict__ bytes,
+                     const int64_t* __restrict__ offsets, int32_t* __restrict__ syms, int64_t sym_stride, int P) {
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= rp.n_outer) return;
+    const int Ts = tokens_of(rp, s);
+    if (Ts <= 0) return;
+    const int CL = 1 << cl_log2, words = kSummHdr + (kWarps << cl_log2), groups = V / VEC;
+    auto seg = [&](int gw) { return (int)(((int64_t)gw * groups) >> (5 + cl_log2)); };  // RowEngine::seg_begin
+    int64_t low = state[s].low, high = state[s].high, value = state[s].value;
+    uint64_t pos = state[s].pos;
+    const uint8_t* data = bytes + offsets[s];
+    const uint64_t nbytes = (uint64_t)(offsets[s + 1] - offsets[s]);
+    uint64_t wb = pos >> 3;  // the window: stream bytes [wb, wb + 24), big-endian words
+    uint64_t hi64 = load_be64(data, nbytes, wb), lo64 = load_be64(data, nbytes, wb + 8);
+    uint64_t nx64 = load_be64(data, nbytes, wb + 16);
+    const float* row = rp.base + s * rp.so;
+    const uint64_t* tab = summ + (s * rp.T) * words;
+    for (int t = 0; t < Ts; t++, tab += words, row += rp.st) {
+        const uint64_t h0 = tab[0], h1 = tab[1];
+        lq::Scale sc;
+        sc.Q = 0;
+        sc.R = (uint32_t)(h0 >> 32);
+        sc.s = (int)(uint32_t)h1;
+        const int nref = (int)(uint32_t)h0;
+        const uint64_t w = (uint64_t)(high - low + 1), xr = (uint64_t)(value - low);
+        const uint32_t target = lq::div_q32(xr >> 32, xr << 32, w);
+        // ---- level 1: lane l looks at warp segments l * CL .. l * CL + CL - 1
+        int best = -1;
+        uint64_t Cb = 0;
+        for (int j = 0; j < CL; j++) {
+            const int gw = (lane << cl_log2) + j;
+            const uint64_t C = tab[kSummHdr + gw];
+            const int gb = seg(gw), ge = seg(gw + 1);
+            if (gb < ge && lq::cum_of(C, (uint32_t)(gb * VEC), sc) <= target) {
+                best = gw;
+                Cb = C;
+            }
+        }
+        const int gsel = __reduce_max_sync(0xffffffffu, best);  // >= 0: the first non-empty segment starts at cum 0
+        Cb = __shfl_sync(0xffffffffu, Cb, gsel >> cl_log2);
+        const int e0 = seg(gsel) * VEC + 32 * lane, eend = seg(gsel + 1) * VEC;
+        // ---- level 2: q of this lane's 32 consecutive elements
+        uint32_t r[kPerThread];
+        if (VEC == 4) {
+            float4 x[kPerThread / 4];
+#pragma unroll
+            for (int p = 0; p < kPerThread / 4; p++) {
+                x[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (e0 + 4 * p < eend) x[p] = __ldg(reinterpret_cast<const float4*>(row + e0 + 4 * p));
+            }
+#pragma unroll
+            for (int p = 0; p < kPerThread / 4; p++) {
+                const bool in = e0 + 4 * p < eend;
+                r[4 * p] = in ? lq::q_of(x[p].x, nref) : 0u;
+                r[4 * p + 1] = in ? lq::q_of(x[p].y, nref) : 0u;
+                r[4 * p + 2] = in ? lq::q_of(x[p].z, nref) : 0u;
+                r[4 * p + 3] = in ? lq::q_of(x[p].w, nref) : 0u;
+            }
+        } else {
+            float x[kPerThread];
+#pragma unroll
+            for (int j = 0; j < kPerThread; j++) x[j] = (e0 + j < eend) ? __ldg(row + e0 + j) : 0.f;
+#pragma unroll
+            for (int j = 0; j < kPerThread; j++) r[j] = (e0 + j < eend) ? lq::q_of(x[j], nref) : 0u;
+        }
+        uint32_t s4[kPerThread / 4];  // sums of 4 consecutive elements (< 2^31.5)
+        uint64_t L = 0;
+#pragma unroll
+        for (int p = 0; p < kPerThread / 4; p++) {
+            s4[p] = (r[4 * p] + r[4 * p + 1]) + (r[4 * p + 2] + r[4 * p + 3]);
+            L += s4[p];
+        }
+        const uint64_t inc = warp_incl_scan(L, lane);
+        const uint64_t Cl = Cb + inc - L;
+        const bool ok = e0 < eend && lq::cum_of(Cl, (uint32_t)e0, sc) <= target;
+        const unsigned ball = __ballot_sync(0xffffffffu, ok);  // lane 0 always qualifies (same test as level 1)
+        const int src = 31 - __clz((int)ball);
+        // ---- inside each lane (only lane `src` matters): last group of 4 whose start qualifies, then the last
+        // element of that group
+        uint64_t Cp = Cl, Cg = Cl;
+        int psel = 0;
+#pragma unroll
+        for (int p = 1; p < kPerThread / 4; p++) {
+            Cp += s4[p - 1];
+            if (e0 + 4 * p < eend && lq::cum_of(Cp, (uint32_t)(e0 + 4 * p), sc) <= target) {
+                psel = p;
+                Cg = Cp;
+            }
+        }
+        uint32_t qe[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int p = 0; p < kPerThread / 4; p++) {
+            if (p == psel) {
+#pragma unroll
+                for (int e = 0; e < 4; e++) qe[e] = r[4 * p + e];
+            }
+        }
+        const int eg = e0 + 4 * psel;
+        int sym = eg;
+        uint64_t Cs = Cg, Ce = Cg;
+        uint32_t qsym = qe[0];
+#pragma unroll
+        for (int e = 1; e < 4; e++) {
+            Ce += qe[e - 1];
+            if (eg + e < eend && lq::cum_of(Ce, (uint32_t)(eg + e), sc) <= target) {
+                sym = eg + e;
+                Cs = Ce;
+                qsym = qe[e];
+            }
+        }
+        uint32_t lo = lq::cum_of(Cs, (uint32_t)sym, sc);
+        uint32_t hi = (sym == V - 1) ? 0u : lq::cum_of(Cs + qsym, (uint32_t)sym + 1, sc);
+        sym = __shfl_sync(0xffffffffu, sym, src);
+        lo = __shfl_sync(0xffffffffu, lo, src);
+        hi = __shfl_sync(0xffffffffu, hi, src);
+        // ---- A_from_bin.emit_symbol + emit_bit loop (arith_code.py:278-298), the same in every lane
+        int64_t nl = low, nh = high;
+        coder::ac_narrow32(nl, nh, lo, hi);
+        const int64_t off = value - nl;  // the value stays inside [nl, nh]
+        const int k = coder::renorm_count((uint64_t)(nh - nl + 1), P);
+        coder::renorm_apply(nl, nh, P, k);
+        const int o = (int)(pos - (wb << 3));  // next k bits from the window (k <= 60, o < 64)
+        const uint64_t comb = o ? ((hi64 << o) | (lo64 >> (64 - o))) : hi64;
+        const uint64_t nb = k ? (comb >> (64 - k)) : 0;
+        low = nl;
+        high = nh;
+        value = nl + (off << k) + (int64_t)nb;
+        pos += (uint64_t)k;
+        if (o + k >= 64) {  // slide by 8 bytes; the word loaded now is not needed before the next slide
+            hi64 = lo64;
+            lo64 = nx64;
+            wb += 8;
+            nx64 = load_be64(data, nbytes, wb + 16);
+        }
+        if (lane == 0) syms[s * sym_stride + t] = sym;
+    }
+    if (lane == 0) {
+        state[s].low = low;
+        state[s].high = high;
+        state[s].value = value;
+        state[s].pos = pos;
+    }
 }
 
 __global__ void dec_init_kernel(lac_dec_state* state, int64_t n, int P, const uint8_t* bytes,
@@ -984,15 +972,57 @@ cudaError_t launch_build(const float* logits, int64_t rows, int V, int64_t row_s
     LAC_DISPATCH(build_kernel, rows, rp, V, cum)
 }
 
+static cudaError_t launch_summary(const RowParams& rp, int V, int cl, int path, uint64_t* summ, cudaStream_t st) {
+    const int64_t rows = rp.n_outer * rp.T;
+    LAC_DISPATCH(summary_kernel, rows, rp, V, summ)
+}
+
+// Decode = summary pass + serial pass per token chunk.  The summaries live in a stream-ordered scratch allocation
+// (cudaMallocAsync; at most ~64 MB, i.e. ~240k rows of a 32000-element vocabulary per chunk).
 cudaError_t launch_decode(const float* logits, int64_t n_streams, int64_t T, int64_t stream_stride,
                           int64_t tok_stride, int V, const int32_t* ntok, lac_dec_state* state,
                           const uint8_t* bytes, const int64_t* offsets, int32_t* syms, int64_t sym_stride,
                           int P, cudaStream_t st) {
     if (n_streams == 0 || T == 0) return cudaSuccess;
-    const RowParams rp{logits, n_streams, T, stream_stride, tok_stride, ntok};
     int cl = 1;
     const int path = path_for(logits, V, stream_stride, tok_stride, &cl);
-    LAC_DISPATCH(decode_kernel, n_streams, rp, V, state, bytes, offsets, syms, sym_stride, P)
+    if (path < 0) return cudaErrorInvalidValue;
+    int cl_log2 = 0;
+    while ((1 << cl_log2) < cl) cl_log2++;
+    const int64_t words = kSummHdr + (int64_t)cl * kWarps;
+    int64_t tc = ((64ll << 20) / (words * 8)) / n_streams;
+    tc = tc < 1 ? 1 : (tc > T ? T : tc);
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        static bool pool_ready[64] = {};
+        if (dev >= 0 && dev < 64 && !pool_ready[dev]) {  // keep freed scratch cached instead of returning it to the OS
+            cudaMemPool_t mp;
+            uint64_t keep = 1ull << 30;
+            if (cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess)
+                cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+            pool_ready[dev] = true;
+        }
+    }
+    uint64_t* summ = nullptr;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&summ), (size_t)(n_streams * tc * words * 8), st);
+    if (e != cudaSuccess) return e;
+    const unsigned serial_blocks = (unsigned)((n_streams + 3) / 4);
+    for (int64_t t0 = 0; t0 < T && e == cudaSuccess; t0 += tc) {
+        const int64_t tn = T - t0 < tc ? T - t0 : tc;
+        const RowParams rp{logits + t0 * tok_stride, n_streams, tn, stream_stride, tok_stride, ntok, t0};
+        e = launch_summary(rp, V, cl, path, summ, st);
+        if (e != cudaSuccess) break;
+        if (path == 0)
+            decode_serial_kernel<1><<<serial_blocks, 128, 0, st>>>(rp, V, cl_log2, summ, state, bytes, offsets,
+                                                                    syms + t0, sym_stride, P);
+        else
+            decode_serial_kernel<4><<<serial_blocks, 128, 0, st>>>(rp, V, cl_log2, summ, state, bytes, offsets,
+                                                                    syms + t0, sym_stride, P);
+        e = cudaGetLastError();
+    }
+    const cudaError_t ef = cudaFreeAsync(summ, st);
+    return e != cudaSuccess ? e : ef;
 }
 
 cudaError_t launch_dec_init(lac_dec_state* state, int64_t n, int P, const uint8_t* bytes,
