@@ -172,31 +172,25 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+// One message to a peer CTA: the value lands in its shared memory and the same operation completes `bytes` of the
+// transaction count of its mbarrier (st.async, SASS: STAS).  No fence on the sending side -- an
+// st.shared::cluster + mbarrier.arrive.release.cluster pair costs MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR per message,
+// about a microsecond under full memory load, which every CTA of the cluster then waits for.
+__device__ __forceinline__ void st_async_u32(uint32_t addr, uint32_t v, uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(addr), "r"(v),
+                 "r"(bar)
+                 : "memory");
 }
-__device__ __forceinline__ void st_cluster_u64(uint32_t addr, uint64_t v) {
-    asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+__device__ __forceinline__ void st_async_u64(uint32_t addr, uint64_t v, uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u64 [%0], %1, [%2];" ::"r"(addr), "l"(v),
+                 "r"(bar)
+                 : "memory");
 }
-__device__ __forceinline__ uint64_t ld_cluster_u64(uint32_t addr) {
-    uint64_t v;
-    asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t remote_bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAITC_%=:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONEC_%=;\n\t"
-        "bra WAITC_%=;\n\t"
-        "DONEC_%=:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
+// Wait for the messages of the peer CTAs (a transaction barrier armed by this CTA, completed by their st.async).
+// The data is in THIS CTA's shared memory and is read with ordinary shared-memory loads after the wait, so the
+// default CTA-scope acquire is the right one (a cluster-scope acquire makes ptxas emit CCTL.IVALL, an L1D
+// invalidate, after every wait).
+__device__ __forceinline__ void mbar_wait_peers(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -217,8 +211,9 @@ constexpr int kMaxCluster = 8;
 struct Ctl {
     uint64_t full[kMaxChunks];  // TMA chunk landed
     uint64_t done;              // row-level bookkeeping published (phase = row parity)
-    uint64_t cl_max_bar;        // cluster: every CTA's maximum has arrived (count CL)
-    uint64_t cl_sum_bar;        // cluster: every CTA's total has arrived (count CL)
+    uint64_t cl_max_bar[2];     // cluster: every CTA's maximum has arrived (transaction barrier, CL messages per
+    uint64_t cl_sum_bar[2];     // cluster: every CTA's total has arrived    phase); one barrier per row parity, so a
+                                //                                           peer one row ahead cannot alias
     uint64_t cl_Q[2][kMaxCluster];  // per-CTA totals, double-buffered by row parity
     int cl_max[2][kMaxCluster];     // per-CTA maxima (ordered ints)
     int red_max[2][kWarps];     // per-warp maxima (order-preserving ints), double-buffered by row parity
@@ -340,8 +335,10 @@ struct RowEngine {
             g_ctl.arrive = 0;
             for (int i = 0; i < NCH; i++) mbar_init(&g_ctl.full[i], 1);
             mbar_init(&g_ctl.done, 1);
-            mbar_init(&g_ctl.cl_max_bar, CL);
-            mbar_init(&g_ctl.cl_sum_bar, CL);
+            for (int i = 0; i < 2; i++) {
+                mbar_init(&g_ctl.cl_max_bar[i], 1);  // one local arrive.expect_tx per phase + CL peer messages
+                mbar_init(&g_ctl.cl_sum_bar[i], 1);
+            }
             fence_mbar_init();
         }
         __syncthreads();
@@ -420,8 +417,9 @@ struct RowEngine {
         __syncthreads();  // the only block-wide barrier of the row
         int mx = __reduce_max_sync(0xffffffffu, red[lane()]);
         if (CL > 1 && threadIdx.x < CL) {  // send this CTA's maximum to every CTA of the cluster (incl. itself)
-            st_cluster_u32(mapa(smem_u32(&g_ctl.cl_max[par][Clu<CL>::rank()]), threadIdx.x), (uint32_t)mx);
-            mbar_arrive_cluster(mapa(smem_u32(&g_ctl.cl_max_bar), threadIdx.x));
+            if (threadIdx.x == 0) mbar_expect_tx(&g_ctl.cl_max_bar[par], CL * 4);
+            st_async_u32(mapa(smem_u32(&g_ctl.cl_max[par][Clu<CL>::rank()]), threadIdx.x), (uint32_t)mx,
+                         mapa(smem_u32(&g_ctl.cl_max_bar[par]), threadIdx.x));
         }
         // phase B: q against the reference of THIS CTA's maximum, uint32 sums per 4 elements (4 q < 2^31.5).
         // (a degenerate reference -- no finite maximum, +inf, out of range -- pushes every shift count past 31,
@@ -442,7 +440,7 @@ struct RowEngine {
             for (int i = 0; i < kPerThread; i += 2) q_of2(x[i], x[i + 1], nref_u, q[i], q[i + 1]);
             // The other CTAs' maxima arrived while phase B ran.  q against the row-wide reference is the local
             // q shifted by the distance of the two references: floor(floor(a / 2^j) / 2^k) = floor(a / 2^(j+k)).
-            mbar_wait_cluster(&g_ctl.cl_max_bar, par);
+            mbar_wait_peers(&g_ctl.cl_max_bar[par], (it >> 1) & 1);
 #pragma unroll
             for (int p = 0; p < CL; p++) mx = max(mx, g_ctl.cl_max[par][p]);
             const int nref = lq::ref_of_max(ord2f(mx));
@@ -464,7 +462,7 @@ struct RowEngine {
             prev = atomicAdd(&g_ctl.arrive, 1u);
         }
         prev = __shfl_sync(0xffffffffu, prev, 0);
-        if (prev == kWarps - 1) finish_row(V, par, lazy, summ, nrow_u);  // last warp of the row: every wsum[] is visible
+        if (prev == kWarps - 1) finish_row(V, par, (it >> 1) & 1, lazy, summ, nrow_u);  // last warp of the row: every wsum[] is visible
         it++;
     }
 
@@ -473,7 +471,8 @@ struct RowEngine {
     // numbers (the one owner warp) waits for the peers itself, so this warp is not held up.
     // summ (decode, pass 1): row summary = { nref | R << 32, s, prefix[32 * CL] }; lane l of every CTA writes the
     // row-wide exclusive prefix at the start of its warp l, rank 0 writes the two header words.
-    static __device__ __noinline__ void finish_row(int V, uint32_t par, bool lazy, uint64_t* summ, uint32_t nrow_u) {
+    static __device__ __noinline__ void finish_row(int V, uint32_t par, uint32_t ph, bool lazy, uint64_t* summ,
+                                                   uint32_t nrow_u) {
         const int ln = lane();
         fence_acq_rel_cta();
         const uint64_t v = *reinterpret_cast<volatile uint64_t*>(&g_ctl.wsum[ln]);
@@ -482,8 +481,9 @@ struct RowEngine {
         uint64_t base = 0;
         if (CL > 1) {  // exchange the CTA totals; base = total of the lower-ranked CTAs
             if (ln < CL) {
-                st_cluster_u64(mapa(smem_u32(&g_ctl.cl_Q[par][Clu<CL>::rank()]), ln), Q);
-                mbar_arrive_cluster(mapa(smem_u32(&g_ctl.cl_sum_bar), ln));
+                if (ln == 0) mbar_expect_tx(&g_ctl.cl_sum_bar[par], CL * 8);
+                st_async_u64(mapa(smem_u32(&g_ctl.cl_Q[par][Clu<CL>::rank()]), ln), Q,
+                             mapa(smem_u32(&g_ctl.cl_sum_bar[par]), ln));
             }
             if (lazy) {
                 g_ctl.pref[ln] = inc - v;  // CTA-local prefix; row_totals() adds the lower CTAs
@@ -494,7 +494,7 @@ struct RowEngine {
                 }
                 return;
             }
-            mbar_wait_cluster(&g_ctl.cl_sum_bar, par);
+            mbar_wait_peers(&g_ctl.cl_sum_bar[par], ph);
             uint64_t tot = 0;
 #pragma unroll
             for (int p = 0; p < CL; p++) {
@@ -528,7 +528,7 @@ struct RowEngine {
         base = 0;
         if (CL == 1) return scale();
         const uint32_t par = (it - 1) & 1;
-        mbar_wait_cluster(&g_ctl.cl_sum_bar, par);
+        mbar_wait_peers(&g_ctl.cl_sum_bar[par], ((it - 1) >> 1) & 1);
         uint64_t tot = 0;
 #pragma unroll
         for (int p = 0; p < CL; p++) {
