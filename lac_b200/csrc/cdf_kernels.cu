@@ -35,7 +35,9 @@ namespace lac {
 constexpr int kThreads = 1024;
 constexpr int kWarps = kThreads / 32;
 constexpr int kPerThread = 32;  // row elements held per thread
-constexpr int kSummHdr = 2;     // row summary (decode pass 1): 2 header words, then 32 * CL prefixes (all uint64)
+// Row summary written by decode pass 1, uint64 words: [0] row reference nref, [1 .. CL] the CTAs' totals of q,
+// [1 + CL + 32 c + w] exclusive prefix of q inside CTA c at the start of its warp w.
+__host__ __device__ constexpr int summ_words(int cl) { return 1 + cl + cl * 32; }
 
 // TMA chunks per row.  Measured on B200 (profiles/microbench/tma_stream.cu): every cp.async.bulk costs
 // ~0.2 us of per-SM TMA time regardless of size, so 8 x 16 KB chunks cap at 4.7 TB/s while 2 x 64 KB
@@ -469,8 +471,7 @@ struct RowEngine {
     // Row-level bookkeeping, run by exactly one warp per CTA per row.
     // lazy (lookup in a cluster): only publish this CTA's total and local prefixes; whoever needs the row-wide
     // numbers (the one owner warp) waits for the peers itself, so this warp is not held up.
-    // summ (decode, pass 1): row summary = { nref | R << 32, s, prefix[32 * CL] }; lane l of every CTA writes the
-    // row-wide exclusive prefix at the start of its warp l, rank 0 writes the two header words.
+    // summ (decode, pass 1): row summary = { nref, total[CL], prefix[CL][32] } (see summ_words()).
     static __device__ __noinline__ void finish_row(int V, uint32_t par, uint32_t ph, bool lazy, uint64_t* summ,
                                                    uint32_t nrow_u) {
         const int ln = lane();
@@ -478,6 +479,19 @@ struct RowEngine {
         const uint64_t v = *reinterpret_cast<volatile uint64_t*>(&g_ctl.wsum[ln]);
         const uint64_t inc = warp_incl_scan(v, ln);
         uint64_t Q = __shfl_sync(0xffffffffu, inc, 31);
+        if (summ) {
+            // decode pass 1: this CTA's part of the row summary -- its total and the CTA-local exclusive prefix at
+            // each of its warps.  No exchange with the peers and no division: pass 2 adds the lower CTAs' totals
+            // and derives the scale itself.
+            summ[1 + CL + (int)Clu<CL>::rank() * kWarps + ln] = inc - v;
+            if (ln == 0) {
+                summ[1 + Clu<CL>::rank()] = Q;
+                if (Clu<CL>::rank() == 0) summ[0] = (uint64_t)nrow_u;
+                g_ctl.arrive = 0;
+                mbar_arrive(&g_ctl.done);
+            }
+            return;
+        }
         uint64_t base = 0;
         if (CL > 1) {  // exchange the CTA totals; base = total of the lower-ranked CTAs
             if (ln < CL) {
@@ -507,13 +521,6 @@ struct RowEngine {
         const uint64_t exc = base + inc - v;  // row-wide exclusive prefix at the start of local warp `ln`
         g_ctl.pref[ln] = exc;
         const lq::Scale sc = lq::make_scale(Q, V);  // one division, the same in every lane
-        if (summ) {
-            summ[kSummHdr + (int)Clu<CL>::rank() * kWarps + ln] = exc;
-            if (ln == 0 && Clu<CL>::rank() == 0) {
-                summ[0] = (uint64_t)nrow_u | ((uint64_t)sc.R << 32);
-                summ[1] = (uint64_t)(uint32_t)sc.s;
-            }
-        }
         __syncwarp();
         if (ln == 0) {
             g_ctl.Q = Q;
@@ -687,7 +694,8 @@ __device__ __forceinline__ uint64_t load_be64(const uint8_t* data, uint64_t nbyt
 
 // ---- pass 1: row summaries.  The same engine as LOOKUP without an owner: rows are dealt to the CTAs / clusters
 // regardless of their stream (a 4-stream job still fills the machine), and the only output is the summary the
-// finishing warp writes -- 16 + 256 * CL bytes per row next to the 4 * V bytes read.
+// finishing warp of each CTA writes -- 8 + 264 * CL bytes per row next to the 4 * V bytes read.  No division and,
+// in a cluster, no exchange of totals: the only cluster traffic left is the row maximum.
 template <int VEC, bool TMA, int NCH, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 summary_kernel(const __grid_constant__ RowParams rp, int V, uint64_t* __restrict__ summ) {
@@ -698,7 +706,7 @@ summary_kernel(const __grid_constant__ RowParams rp, int V, uint64_t* __restrict
     seq.init(rp, Clu<CL>::id(), Clu<CL>::count());
     if (seq.valid(rp)) Eng::issue(seq.ptr(rp), V);
     while (seq.valid(rp)) {
-        uint64_t* out = summ + seq.index(rp) * (kSummHdr + CL * kWarps);
+        uint64_t* out = summ + seq.index(rp) * summ_words(CL);
         const float* row = seq.ptr(rp);
         seq.next(rp);
         uint32_t q[kPerThread];
@@ -726,7 +734,7 @@ decode_serial_kernel(const __grid_constant__ RowParams rp, int V, int cl_log2, c
     if (s >= rp.n_outer) return;
     const int Ts = tokens_of(rp, s);
     if (Ts <= 0) return;
-    const int CL = 1 << cl_log2, words = kSummHdr + (kWarps << cl_log2), groups = V / VEC;
+    const int CL = 1 << cl_log2, words = summ_words(CL), groups = V / VEC;
     auto seg = [&](int gw) { return (int)(((int64_t)gw * groups) >> (5 + cl_log2)); };  // RowEngine::seg_begin
     int64_t low = state[s].low, high = state[s].high, value = state[s].value;
     uint64_t pos = state[s].pos;
@@ -738,28 +746,27 @@ decode_serial_kernel(const __grid_constant__ RowParams rp, int V, int cl_log2, c
     const float* row = rp.base + s * rp.so;
     const uint64_t* tab = summ + (s * rp.T) * words;
     for (int t = 0; t < Ts; t++, tab += words, row += rp.st) {
-        const uint64_t h0 = tab[0], h1 = tab[1];
-        lq::Scale sc;
-        sc.Q = 0;
-        sc.R = (uint32_t)(h0 >> 32);
-        sc.s = (int)(uint32_t)h1;
-        const int nref = (int)(uint32_t)h0;
+        const int nref = (int)(uint32_t)tab[0];
+        uint64_t Q = 0;
+        for (int c = 0; c < CL; c++) Q += tab[1 + c];
+        const lq::Scale sc = lq::make_scale(Q, V);  // independent of the coder state: overlaps the probe division
         const uint64_t w = (uint64_t)(high - low + 1), xr = (uint64_t)(value - low);
         const uint32_t target = lq::div_q32(xr >> 32, xr << 32, w);
-        // ---- level 1: lane l looks at warp segments l * CL .. l * CL + CL - 1
+        // ---- level 1: lane l looks at warp l of every CTA part (row-wide warp 32 c + l)
         int best = -1;
-        uint64_t Cb = 0;
-        for (int j = 0; j < CL; j++) {
-            const int gw = (lane << cl_log2) + j;
-            const uint64_t C = tab[kSummHdr + gw];
+        uint64_t Cb = 0, base = 0;
+        for (int c = 0; c < CL; c++) {
+            const int gw = 32 * c + lane;
+            const uint64_t C = base + tab[1 + CL + gw];
             const int gb = seg(gw), ge = seg(gw + 1);
             if (gb < ge && lq::cum_of(C, (uint32_t)(gb * VEC), sc) <= target) {
                 best = gw;
                 Cb = C;
             }
+            base += tab[1 + c];
         }
         const int gsel = __reduce_max_sync(0xffffffffu, best);  // >= 0: the first non-empty segment starts at cum 0
-        Cb = __shfl_sync(0xffffffffu, Cb, gsel >> cl_log2);
+        Cb = __shfl_sync(0xffffffffu, Cb, gsel & 31);
         const int e0 = seg(gsel) * VEC + 32 * lane, eend = seg(gsel + 1) * VEC;
         // ---- level 2: q of this lane's 32 consecutive elements
         uint32_t r[kPerThread];
@@ -989,7 +996,7 @@ cudaError_t launch_decode(const float* logits, int64_t n_streams, int64_t T, int
     if (path < 0) return cudaErrorInvalidValue;
     int cl_log2 = 0;
     while ((1 << cl_log2) < cl) cl_log2++;
-    const int64_t words = kSummHdr + (int64_t)cl * kWarps;
+    const int64_t words = summ_words(cl);
     int64_t tc = ((64ll << 20) / (words * 8)) / n_streams;
     tc = tc < 1 ? 1 : (tc > T ? T : tc);
     {
