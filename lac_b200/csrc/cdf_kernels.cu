@@ -365,7 +365,7 @@ struct RowEngine {
     // (g_ctl.pref, Q, R, s) are valid once wait_done() returns.  summ != nullptr: the finishing warp also writes
     // the row summary (reference, scale, warp-segment prefixes) there.
     __device__ __forceinline__ void reduce(const float* __restrict__ row, const float* next_row, int V,
-                                           uint32_t (&q)[kPerThread], bool lazy = false, uint64_t* summ = nullptr) {
+                                           uint32_t (&q)[kPerThread], uint64_t* summ = nullptr) {
         float x[kPerThread];
         {
             const int gb = gbeg(V), ge = gend(V), ln = lane();
@@ -464,15 +464,13 @@ struct RowEngine {
             prev = atomicAdd(&g_ctl.arrive, 1u);
         }
         prev = __shfl_sync(0xffffffffu, prev, 0);
-        if (prev == kWarps - 1) finish_row(V, par, (it >> 1) & 1, lazy, summ, nrow_u);  // last warp of the row: every wsum[] is visible
+        if (prev == kWarps - 1) finish_row(V, par, (it >> 1) & 1, summ, nrow_u);  // last warp of the row: every wsum[] is visible
         it++;
     }
 
     // Row-level bookkeeping, run by exactly one warp per CTA per row.
-    // lazy (lookup in a cluster): only publish this CTA's total and local prefixes; whoever needs the row-wide
-    // numbers (the one owner warp) waits for the peers itself, so this warp is not held up.
     // summ (decode, pass 1): row summary = { nref, total[CL], prefix[CL][32] } (see summ_words()).
-    static __device__ __noinline__ void finish_row(int V, uint32_t par, uint32_t ph, bool lazy, uint64_t* summ,
+    static __device__ __noinline__ void finish_row(int V, uint32_t par, uint32_t ph, uint64_t* summ,
                                                    uint32_t nrow_u) {
         const int ln = lane();
         fence_acq_rel_cta();
@@ -499,15 +497,6 @@ struct RowEngine {
                 st_async_u64(mapa(smem_u32(&g_ctl.cl_Q[par][Clu<CL>::rank()]), ln), Q,
                              mapa(smem_u32(&g_ctl.cl_sum_bar[par]), ln));
             }
-            if (lazy) {
-                g_ctl.pref[ln] = inc - v;  // CTA-local prefix; row_totals() adds the lower CTAs
-                __syncwarp();
-                if (ln == 0) {
-                    g_ctl.arrive = 0;
-                    mbar_arrive(&g_ctl.done);
-                }
-                return;
-            }
             mbar_wait_peers(&g_ctl.cl_sum_bar[par], ph);
             uint64_t tot = 0;
 #pragma unroll
@@ -530,21 +519,6 @@ struct RowEngine {
             mbar_arrive(&g_ctl.done);  // release: publishes everything above
         }
     }
-    // Lazy mode, called by one lane after wait_done(): row total, this CTA's base, and the scale.
-    __device__ __forceinline__ lq::Scale row_totals(int V, uint64_t& base) const {
-        base = 0;
-        if (CL == 1) return scale();
-        const uint32_t par = (it - 1) & 1;
-        mbar_wait_peers(&g_ctl.cl_sum_bar[par], ((it - 1) >> 1) & 1);
-        uint64_t tot = 0;
-#pragma unroll
-        for (int p = 0; p < CL; p++) {
-            const uint64_t qp = g_ctl.cl_Q[par][p];
-            if (p < (int)Clu<CL>::rank()) base += qp;
-            tot += qp;
-        }
-        return lq::make_scale(tot, V);
-    }
     // Block until the row-level results of the row just reduce()d are published.
     __device__ __forceinline__ void wait_done() const { mbar_wait(&g_ctl.done, (it - 1) & 1); }
     static __device__ __forceinline__ lq::Scale scale() {
@@ -556,64 +530,72 @@ struct RowEngine {
     }
 };
 
-// ------------------------------------------------------------------ LOOKUP
-template <int VEC, bool TMA, int NCH, int CL>
-__global__ void __launch_bounds__(kThreads, 1)
-lookup_kernel(const __grid_constant__ RowParams rp, int V, const int32_t* __restrict__ syms,
-              uint32_t* __restrict__ pairs, uint32_t* __restrict__ status) {
-    using Eng = RowEngine<VEC, TMA, NCH, CL>;
-    Ctl& ctl = g_ctl;
-    Eng eng;
-    eng.setup();
-    const uint32_t stride = Clu<CL>::count();
-    RowSeq seq;
-    seq.init(rp, Clu<CL>::id(), stride);
-    if (seq.valid(rp)) Eng::issue(seq.ptr(rp), V);
-    while (seq.valid(rp)) {
-        const int64_t r = seq.s;
-        const float* row = seq.ptr(rp);
-        const int sym = __ldg(syms + r);  // issued now, consumed after the row's compute phases
-        seq.next(rp, stride);
-        uint32_t q[kPerThread];
-        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, V, q, CL > 1);
-        const int warp = Eng::warp(), lane = Eng::lane(), gbeg = Eng::gbeg(V), gend = Eng::gend(V);
-        if (sym < 0 || sym >= V) {
-            if (threadIdx.x == 0 && Clu<CL>::rank() == 0) {
-                *reinterpret_cast<uint2*>(pairs + 2 * r) = make_uint2(0u, 0u);
-                if (status) atomicOr(status + r, LAC_ST_SYMBOL);
-            }
-            continue;
+// ------------------------------------------------------------------ LOOKUP (encode side, second pass)
+// symbol_to_range (arith_code.py:87-93) on the total 2^32 for one coded symbol per row: (cum[sym], cum[sym + 1]).
+// Pass 1 is summary_kernel (below); this pass is one warp per row, all rows independent: find the warp segment
+// of the symbol, re-read the part of it in front of the symbol (<= 4 KB, half of that on average), q against the
+// row reference, masked integer sums, two multiply-shifts.  ~3 % extra HBM traffic, a few microseconds per 16k rows.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+pair_kernel(const float* __restrict__ logits, int64_t rows, int64_t row_stride, int V, int cl_log2,
+            const uint64_t* __restrict__ summ, const int32_t* __restrict__ syms, uint32_t* __restrict__ pairs,
+            uint32_t* __restrict__ status) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int sym = __ldg(syms + r);
+    if (sym < 0 || sym >= V) {
+        if (lane == 0) {
+            *reinterpret_cast<uint2*>(pairs + 2 * r) = make_uint2(0u, 0u);
+            if (status) atomicOr(status + r, LAC_ST_SYMBOL);
         }
-        const int gs = sym / VEC, es = sym % VEC;
-        if (gs >= gbeg && gs < gend) {  // owner warp; everyone else is already on the next row
-            uint64_t part = 0, qs = 0;
-            constexpr int IT = kPerThread / VEC;
-#pragma unroll
-            for (int k = 0; k < IT; k++) {
-                int g = gbeg + k * 32 + lane;
-#pragma unroll
-                for (int e = 0; e < VEC; e++) {
-                    uint32_t v = q[k * VEC + e];
-                    if (g < gs || (g == gs && e < es)) part += v;
-                    if (g == gs && e == es) qs = v;
-                }
+        return;
+    }
+    const int CL = 1 << cl_log2, groups = V / VEC, tw = kWarps << cl_log2;
+    auto seg = [&](int gw) { return (int)(((int64_t)gw * groups) >> (5 + cl_log2)); };  // RowEngine::seg_begin
+    const uint64_t* tab = summ + r * summ_words(CL);
+    const int gs = sym / VEC;
+    int gw = (int)(((int64_t)gs * tw) / groups);  // the row-wide warp whose segment holds group gs (+- 1)
+    gw = gw >= tw ? tw - 1 : gw;
+    while (seg(gw + 1) <= gs) gw++;
+    while (seg(gw) > gs) gw--;
+    const int nref = (int)(uint32_t)tab[0];
+    uint64_t Q = 0, C = tab[1 + CL + gw];
+    for (int c = 0; c < CL; c++) {
+        const uint64_t tot = tab[1 + c];
+        Q += tot;
+        if (c < (gw >> 5)) C += tot;
+    }
+    const lq::Scale sc = lq::make_scale(Q, V);
+    const float* row = logits + r * row_stride;
+    uint64_t part = 0;
+    uint32_t qs = 0;
+    for (int g = seg(gw) + lane; g <= gs; g += 32) {  // groups in front of (and including) the symbol's group
+        if (VEC == 4) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(row) + g);
+            const uint32_t q0 = lq::q_of(x.x, nref), q1 = lq::q_of(x.y, nref), q2 = lq::q_of(x.z, nref),
+                           q3 = lq::q_of(x.w, nref);
+            if (g < gs) {
+                part += (uint64_t)((q0 + q1) + (q2 + q3));
+            } else {
+                const int es = sym & 3;
+                part += (uint64_t)(es > 0 ? q0 : 0u) + (es > 1 ? q1 : 0u) + (es > 2 ? q2 : 0u);
+                qs = es == 0 ? q0 : es == 1 ? q1 : es == 2 ? q2 : q3;
             }
-            part = warp_sum48(part);
-            qs = warp_sum48(qs);
-            eng.wait_done();
-            if (lane == 0) {
-                uint64_t base;
-                const lq::Scale sc = eng.row_totals(V, base);
-                const uint64_t C = base + ctl.pref[warp] + part;
-                uint2 o;
-                o.x = lq::cum_of(C, (uint32_t)sym, sc);
-                o.y = (sym == V - 1) ? 0u : lq::cum_of(C + qs, (uint32_t)sym + 1, sc);
-                *reinterpret_cast<uint2*>(pairs + 2 * r) = o;
-            }
-            __syncwarp();
+        } else {
+            const uint32_t q0 = lq::q_of(__ldg(row + g), nref);
+            if (g < gs) part += q0;
+            else qs = q0;
         }
     }
-    Eng::teardown();
+    part = warp_sum48(part);
+    qs = __reduce_add_sync(0xffffffffu, qs);  // exactly one lane holds the symbol
+    if (lane == 0) {
+        uint2 o;
+        o.x = lq::cum_of(C + part, (uint32_t)sym, sc);
+        o.y = (sym == V - 1) ? 0u : lq::cum_of(C + part + qs, (uint32_t)sym + 1, sc);
+        *reinterpret_cast<uint2*>(pairs + 2 * r) = o;
+    }
 }
 
 // ------------------------------------------------------------------ BUILD
@@ -710,7 +692,7 @@ summary_kernel(const __grid_constant__ RowParams rp, int V, uint64_t* __restrict
         const float* row = seq.ptr(rp);
         seq.next(rp);
         uint32_t q[kPerThread];
-        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, V, q, false, out);
+        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, V, q, out);
     }
     Eng::teardown();
 }
@@ -961,15 +943,6 @@ static int plain_grid(int64_t units) {
     }                                                                                                                 \
     return cudaGetLastError();
 
-cudaError_t launch_lookup(const float* logits, int64_t rows, int V, int64_t row_stride, const int32_t* syms,
-                          uint32_t* pairs, uint32_t* status, cudaStream_t st) {
-    if (rows == 0) return cudaSuccess;
-    const RowParams rp{logits, rows, 1, row_stride, 0, nullptr};
-    int cl = 1;
-    const int path = path_for(logits, V, row_stride, 0, &cl);
-    LAC_DISPATCH(lookup_kernel, rows, rp, V, syms, pairs, status)
-}
-
 cudaError_t launch_build(const float* logits, int64_t rows, int V, int64_t row_stride, uint32_t* cum,
                          cudaStream_t st) {
     if (rows == 0) return cudaSuccess;
@@ -984,8 +957,57 @@ static cudaError_t launch_summary(const RowParams& rp, int V, int cl, int path, 
     LAC_DISPATCH(summary_kernel, rows, rp, V, summ)
 }
 
-// Decode = summary pass + serial pass per token chunk.  The summaries live in a stream-ordered scratch allocation
-// (cudaMallocAsync; at most ~64 MB, i.e. ~240k rows of a 32000-element vocabulary per chunk).
+// Row summaries live in a stream-ordered scratch allocation (cudaMallocAsync), at most ~64 MB per chunk of rows.
+static cudaError_t summ_alloc(uint64_t** summ, int64_t rows, int cl, cudaStream_t st) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool pool_ready[64] = {};
+    if (dev >= 0 && dev < 64 && !pool_ready[dev]) {  // keep freed scratch cached instead of returning it to the OS
+        cudaMemPool_t mp;
+        uint64_t keep = 1ull << 30;
+        if (cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess)
+            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+        pool_ready[dev] = true;
+    }
+    return cudaMallocAsync(reinterpret_cast<void**>(summ), (size_t)(rows * summ_words(cl) * 8), st);
+}
+static int64_t summ_chunk_rows(int cl) { return (64ll << 20) / (summ_words(cl) * 8); }
+static int log2_of(int cl) {
+    int l = 0;
+    while ((1 << l) < cl) l++;
+    return l;
+}
+
+// Encode side: summary pass + one warp per row for the pair.
+cudaError_t launch_lookup(const float* logits, int64_t rows, int V, int64_t row_stride, const int32_t* syms,
+                          uint32_t* pairs, uint32_t* status, cudaStream_t st) {
+    if (rows == 0) return cudaSuccess;
+    int cl = 1;
+    const int path = path_for(logits, V, row_stride, 0, &cl);
+    if (path < 0) return cudaErrorInvalidValue;
+    const int64_t chunk = rows < summ_chunk_rows(cl) ? rows : summ_chunk_rows(cl);
+    uint64_t* summ = nullptr;
+    cudaError_t e = summ_alloc(&summ, chunk, cl, st);
+    if (e != cudaSuccess) return e;
+    for (int64_t r0 = 0; r0 < rows && e == cudaSuccess; r0 += chunk) {
+        const int64_t rn = rows - r0 < chunk ? rows - r0 : chunk;
+        const float* base = logits + r0 * row_stride;
+        const RowParams rp{base, rn, 1, row_stride, 0, nullptr, 0};
+        e = launch_summary(rp, V, cl, path, summ, st);
+        if (e != cudaSuccess) break;
+        const unsigned blocks = (unsigned)((rn + 7) / 8);
+        uint32_t* stat = status ? status + r0 : nullptr;
+        if (path == 0)
+            pair_kernel<1><<<blocks, 256, 0, st>>>(base, rn, row_stride, V, log2_of(cl), summ, syms + r0, pairs + 2 * r0, stat);
+        else
+            pair_kernel<4><<<blocks, 256, 0, st>>>(base, rn, row_stride, V, log2_of(cl), summ, syms + r0, pairs + 2 * r0, stat);
+        e = cudaGetLastError();
+    }
+    const cudaError_t ef = cudaFreeAsync(summ, st);
+    return e != cudaSuccess ? e : ef;
+}
+
+// Decode = summary pass + serial pass per token chunk (~240k rows of a 32000-element vocabulary per chunk).
 cudaError_t launch_decode(const float* logits, int64_t n_streams, int64_t T, int64_t stream_stride,
                           int64_t tok_stride, int V, const int32_t* ntok, lac_dec_state* state,
                           const uint8_t* bytes, const int64_t* offsets, int32_t* syms, int64_t sym_stride,
@@ -994,25 +1016,11 @@ cudaError_t launch_decode(const float* logits, int64_t n_streams, int64_t T, int
     int cl = 1;
     const int path = path_for(logits, V, stream_stride, tok_stride, &cl);
     if (path < 0) return cudaErrorInvalidValue;
-    int cl_log2 = 0;
-    while ((1 << cl_log2) < cl) cl_log2++;
-    const int64_t words = summ_words(cl);
-    int64_t tc = ((64ll << 20) / (words * 8)) / n_streams;
+    const int cl_log2 = log2_of(cl);
+    int64_t tc = summ_chunk_rows(cl) / n_streams;
     tc = tc < 1 ? 1 : (tc > T ? T : tc);
-    {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        static bool pool_ready[64] = {};
-        if (dev >= 0 && dev < 64 && !pool_ready[dev]) {  // keep freed scratch cached instead of returning it to the OS
-            cudaMemPool_t mp;
-            uint64_t keep = 1ull << 30;
-            if (cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess)
-                cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
-            pool_ready[dev] = true;
-        }
-    }
     uint64_t* summ = nullptr;
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&summ), (size_t)(n_streams * tc * words * 8), st);
+    cudaError_t e = summ_alloc(&summ, n_streams * tc, cl, st);
     if (e != cudaSuccess) return e;
     const unsigned serial_blocks = (unsigned)((n_streams + 3) / 4);
     for (int64_t t0 = 0; t0 < T && e == cudaSuccess; t0 += tc) {
