@@ -707,7 +707,7 @@ summary_kernel(const __grid_constant__ RowParams rp, int V, uint64_t* __restrict
 //   update   narrow, renormalise by k bits at once, pull k bits from a 24-byte register window of the stream
 // The logits segment comes from HBM (pass 1 streamed the rows with evict-first), ~3 % extra traffic.
 template <int VEC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 1)
 decode_serial_kernel(const __grid_constant__ RowParams rp, int V, int cl_log2, const uint64_t* __restrict__ summ,
                      lac_dec_state* __restrict__ state, const uint8_t* __restrict__ bytes,
                      const int64_t* __restrict__ offsets, int32_t* __restrict__ syms, int64_t sym_stride, int P) {
@@ -750,29 +750,34 @@ decode_serial_kernel(const __grid_constant__ RowParams rp, int V, int cl_log2, c
         const int gsel = __reduce_max_sync(0xffffffffu, best);  // >= 0: the first non-empty segment starts at cum 0
         Cb = __shfl_sync(0xffffffffu, Cb, gsel & 31);
         const int e0 = seg(gsel) * VEC + 32 * lane, eend = seg(gsel + 1) * VEC;
-        // ---- level 2: q of this lane's 32 consecutive elements
+        // ---- level 2: q of this lane's 32 consecutive elements.  All loads first (unconditional, from addresses
+        // clamped into the segment), then branch-free arithmetic: the HBM latency is paid once per token.
         uint32_t r[kPerThread];
         if (VEC == 4) {
+            const int glast = eend - 4;  // the segment is not empty
             float4 x[kPerThread / 4];
 #pragma unroll
-            for (int p = 0; p < kPerThread / 4; p++) {
-                x[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (e0 + 4 * p < eend) x[p] = __ldg(reinterpret_cast<const float4*>(row + e0 + 4 * p));
-            }
+            for (int p = 0; p < kPerThread / 4; p++)
+                x[p] = __ldg(reinterpret_cast<const float4*>(row + min(e0 + 4 * p, glast)));
 #pragma unroll
             for (int p = 0; p < kPerThread / 4; p++) {
-                const bool in = e0 + 4 * p < eend;
-                r[4 * p] = in ? lq::q_of(x[p].x, nref) : 0u;
-                r[4 * p + 1] = in ? lq::q_of(x[p].y, nref) : 0u;
-                r[4 * p + 2] = in ? lq::q_of(x[p].z, nref) : 0u;
-                r[4 * p + 3] = in ? lq::q_of(x[p].w, nref) : 0u;
+                const uint32_t m = (e0 + 4 * p < eend) ? 0xFFFFFFFFu : 0u;
+                q_of2(x[p].x, x[p].y, (uint32_t)nref, r[4 * p], r[4 * p + 1]);
+                q_of2(x[p].z, x[p].w, (uint32_t)nref, r[4 * p + 2], r[4 * p + 3]);
+#pragma unroll
+                for (int e = 0; e < 4; e++) r[4 * p + e] &= m;
             }
         } else {
+            const int elast = eend - 1;
             float x[kPerThread];
 #pragma unroll
-            for (int j = 0; j < kPerThread; j++) x[j] = (e0 + j < eend) ? __ldg(row + e0 + j) : 0.f;
+            for (int j = 0; j < kPerThread; j++) x[j] = __ldg(row + min(e0 + j, elast));
 #pragma unroll
-            for (int j = 0; j < kPerThread; j++) r[j] = (e0 + j < eend) ? lq::q_of(x[j], nref) : 0u;
+            for (int j = 0; j < kPerThread; j += 2) {
+                q_of2(x[j], x[j + 1], (uint32_t)nref, r[j], r[j + 1]);
+                r[j] &= (e0 + j < eend) ? 0xFFFFFFFFu : 0u;
+                r[j + 1] &= (e0 + j + 1 < eend) ? 0xFFFFFFFFu : 0u;
+            }
         }
         uint32_t s4[kPerThread / 4];  // sums of 4 consecutive elements (< 2^31.5)
         uint64_t L = 0;
@@ -783,28 +788,25 @@ decode_serial_kernel(const __grid_constant__ RowParams rp, int V, int cl_log2, c
         }
         const uint64_t inc = warp_incl_scan(L, lane);
         const uint64_t Cl = Cb + inc - L;
-        const bool ok = e0 < eend && lq::cum_of(Cl, (uint32_t)e0, sc) <= target;
+        const bool ok = (e0 < eend) & (lq::cum_of(Cl, (uint32_t)e0, sc) <= target);
         const unsigned ball = __ballot_sync(0xffffffffu, ok);  // lane 0 always qualifies (same test as level 1)
         const int src = 31 - __clz((int)ball);
-        // ---- inside each lane (only lane `src` matters): last group of 4 whose start qualifies, then the last
-        // element of that group
+        // ---- inside each lane (only lane `src` matters), branch-free: last group of 4 whose start qualifies,
+        // then the last element of that group
         uint64_t Cp = Cl, Cg = Cl;
         int psel = 0;
 #pragma unroll
         for (int p = 1; p < kPerThread / 4; p++) {
             Cp += s4[p - 1];
-            if (e0 + 4 * p < eend && lq::cum_of(Cp, (uint32_t)(e0 + 4 * p), sc) <= target) {
-                psel = p;
-                Cg = Cp;
-            }
+            const bool okp = (e0 + 4 * p < eend) & (lq::cum_of(Cp, (uint32_t)(e0 + 4 * p), sc) <= target);
+            psel = okp ? p : psel;
+            Cg = okp ? Cp : Cg;
         }
-        uint32_t qe[4] = {0u, 0u, 0u, 0u};
+        uint32_t qe[4] = {r[0], r[1], r[2], r[3]};
 #pragma unroll
-        for (int p = 0; p < kPerThread / 4; p++) {
-            if (p == psel) {
+        for (int p = 1; p < kPerThread / 4; p++) {
 #pragma unroll
-                for (int e = 0; e < 4; e++) qe[e] = r[4 * p + e];
-            }
+            for (int e = 0; e < 4; e++) qe[e] = (p == psel) ? r[4 * p + e] : qe[e];
         }
         const int eg = e0 + 4 * psel;
         int sym = eg;
@@ -813,11 +815,10 @@ decode_serial_kernel(const __grid_constant__ RowParams rp, int V, int cl_log2, c
 #pragma unroll
         for (int e = 1; e < 4; e++) {
             Ce += qe[e - 1];
-            if (eg + e < eend && lq::cum_of(Ce, (uint32_t)(eg + e), sc) <= target) {
-                sym = eg + e;
-                Cs = Ce;
-                qsym = qe[e];
-            }
+            const bool oke = (eg + e < eend) & (lq::cum_of(Ce, (uint32_t)(eg + e), sc) <= target);
+            sym = oke ? eg + e : sym;
+            Cs = oke ? Ce : Cs;
+            qsym = oke ? qe[e] : qsym;
         }
         uint32_t lo = lq::cum_of(Cs, (uint32_t)sym, sc);
         uint32_t hi = (sym == V - 1) ? 0u : lq::cum_of(Cs + qsym, (uint32_t)sym + 1, sc);
