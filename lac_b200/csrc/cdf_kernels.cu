@@ -706,9 +706,30 @@ summary_kernel(const __grid_constant__ RowParams rp, int V, uint64_t* __restrict
 //            + ballot picks the lane, the rest of the search is independent work inside each lane
 //   update   narrow, renormalise by k bits at once, pull k bits from a 24-byte register window of the stream
 // The logits segment comes from HBM (pass 1 streamed the rows with evict-first), ~3 % extra traffic.
-template <int VEC>
+// The summary of token t + 1 is loaded while token t is being searched and its scale (the one division that does
+// not depend on the coder state) is computed while token t's segment is in flight.
+template <int CL>
+struct RowTab {
+    uint64_t nref, tot[CL], pre[CL];  // pre: CTA-local prefix at warp `lane` of CTA part c
+    __device__ __forceinline__ void load(const uint64_t* tab, int lane) {
+        nref = tab[0];
+#pragma unroll
+        for (int c = 0; c < CL; c++) {
+            tot[c] = tab[1 + c];
+            pre[c] = tab[1 + CL + 32 * c + lane];
+        }
+    }
+    __device__ __forceinline__ uint64_t total() const {
+        uint64_t Q = 0;
+#pragma unroll
+        for (int c = 0; c < CL; c++) Q += tot[c];
+        return Q;
+    }
+};
+
+template <int VEC, int CL>
 __global__ void __launch_bounds__(128, 1)
-decode_serial_kernel(const __grid_constant__ RowParams rp, int V, int cl_log2, const uint64_t* __restrict__ summ,
+decode_serial_kernel(const __grid_constant__ RowParams rp, int V, const uint64_t* __restrict__ summ,
                      lac_dec_state* __restrict__ state, const uint8_t* __restrict__ bytes,
                      const int64_t* __restrict__ offsets, int32_t* __restrict__ syms, int64_t sym_stride, int P) {
     const int lane = threadIdx.x & 31;
@@ -716,8 +737,9 @@ decode_serial_kernel(const __grid_constant__ RowParams rp, int V, int cl_log2, c
     if (s >= rp.n_outer) return;
     const int Ts = tokens_of(rp, s);
     if (Ts <= 0) return;
-    const int CL = 1 << cl_log2, words = summ_words(CL), groups = V / VEC;
-    auto seg = [&](int gw) { return (int)(((int64_t)gw * groups) >> (5 + cl_log2)); };  // RowEngine::seg_begin
+    constexpr int words = summ_words(CL);
+    const int groups = V / VEC;
+    auto seg = [&](int gw) { return (int)(((int64_t)gw * groups) / (kWarps * CL)); };  // RowEngine::seg_begin
     int64_t low = state[s].low, high = state[s].high, value = state[s].value;
     uint64_t pos = state[s].pos;
     const uint8_t* data = bytes + offsets[s];
@@ -727,31 +749,39 @@ decode_serial_kernel(const __grid_constant__ RowParams rp, int V, int cl_log2, c
     uint64_t nx64 = load_be64(data, nbytes, wb + 16);
     const float* row = rp.base + s * rp.so;
     const uint64_t* tab = summ + (s * rp.T) * words;
+    RowTab<CL> cur, nxt;
+    cur.load(tab, lane);
+    lq::Scale sc = lq::make_scale(cur.total(), V);
+    nxt = cur;
+    if (Ts > 1) nxt.load(tab + words, lane);
     for (int t = 0; t < Ts; t++, tab += words, row += rp.st) {
-        const int nref = (int)(uint32_t)tab[0];
-        uint64_t Q = 0;
-        for (int c = 0; c < CL; c++) Q += tab[1 + c];
-        const lq::Scale sc = lq::make_scale(Q, V);  // independent of the coder state: overlaps the probe division
+        const int nref = (int)(uint32_t)cur.nref;
         const uint64_t w = (uint64_t)(high - low + 1), xr = (uint64_t)(value - low);
         const uint32_t target = lq::div_q32(xr >> 32, xr << 32, w);
         // ---- level 1: lane l looks at warp l of every CTA part (row-wide warp 32 c + l)
         int best = -1;
         uint64_t Cb = 0, base = 0;
+#pragma unroll
         for (int c = 0; c < CL; c++) {
             const int gw = 32 * c + lane;
-            const uint64_t C = base + tab[1 + CL + gw];
+            const uint64_t C = base + cur.pre[c];
             const int gb = seg(gw), ge = seg(gw + 1);
-            if (gb < ge && lq::cum_of(C, (uint32_t)(gb * VEC), sc) <= target) {
-                best = gw;
-                Cb = C;
-            }
-            base += tab[1 + c];
+            const bool okw = (gb < ge) & (lq::cum_of(C, (uint32_t)(gb * VEC), sc) <= target);
+            best = okw ? gw : best;
+            Cb = okw ? C : Cb;
+            base += cur.tot[c];
         }
         const int gsel = __reduce_max_sync(0xffffffffu, best);  // >= 0: the first non-empty segment starts at cum 0
         Cb = __shfl_sync(0xffffffffu, Cb, gsel & 31);
         const int e0 = seg(gsel) * VEC + 32 * lane, eend = seg(gsel + 1) * VEC;
         // ---- level 2: q of this lane's 32 consecutive elements.  All loads first (unconditional, from addresses
         // clamped into the segment), then branch-free arithmetic: the HBM latency is paid once per token.
+        const lq::Scale sc_now = sc;
+        auto advance = [&]() {  // while the segment is in flight: next token's scale, then the summary after that
+            cur = nxt;
+            sc = lq::make_scale(cur.total(), V);
+            if (t + 2 < Ts) nxt.load(tab + 2 * words, lane);
+        };
         uint32_t r[kPerThread];
         if (VEC == 4) {
             const int glast = eend - 4;  // the segment is not empty
@@ -759,6 +789,7 @@ decode_serial_kernel(const __grid_constant__ RowParams rp, int V, int cl_log2, c
 #pragma unroll
             for (int p = 0; p < kPerThread / 4; p++)
                 x[p] = __ldg(reinterpret_cast<const float4*>(row + min(e0 + 4 * p, glast)));
+            advance();
 #pragma unroll
             for (int p = 0; p < kPerThread / 4; p++) {
                 const uint32_t m = (e0 + 4 * p < eend) ? 0xFFFFFFFFu : 0u;
@@ -772,6 +803,7 @@ decode_serial_kernel(const __grid_constant__ RowParams rp, int V, int cl_log2, c
             float x[kPerThread];
 #pragma unroll
             for (int j = 0; j < kPerThread; j++) x[j] = __ldg(row + min(e0 + j, elast));
+            advance();
 #pragma unroll
             for (int j = 0; j < kPerThread; j += 2) {
                 q_of2(x[j], x[j + 1], (uint32_t)nref, r[j], r[j + 1]);
@@ -788,7 +820,7 @@ decode_serial_kernel(const __grid_constant__ RowParams rp, int V, int cl_log2, c
         }
         const uint64_t inc = warp_incl_scan(L, lane);
         const uint64_t Cl = Cb + inc - L;
-        const bool ok = (e0 < eend) & (lq::cum_of(Cl, (uint32_t)e0, sc) <= target);
+        const bool ok = (e0 < eend) & (lq::cum_of(Cl, (uint32_t)e0, sc_now) <= target);
         const unsigned ball = __ballot_sync(0xffffffffu, ok);  // lane 0 always qualifies (same test as level 1)
         const int src = 31 - __clz((int)ball);
         // ---- inside each lane (only lane `src` matters), branch-free: last group of 4 whose start qualifies,
@@ -798,7 +830,7 @@ decode_serial_kernel(const __grid_constant__ RowParams rp, int V, int cl_log2, c
 #pragma unroll
         for (int p = 1; p < kPerThread / 4; p++) {
             Cp += s4[p - 1];
-            const bool okp = (e0 + 4 * p < eend) & (lq::cum_of(Cp, (uint32_t)(e0 + 4 * p), sc) <= target);
+            const bool okp = (e0 + 4 * p < eend) & (lq::cum_of(Cp, (uint32_t)(e0 + 4 * p), sc_now) <= target);
             psel = okp ? p : psel;
             Cg = okp ? Cp : Cg;
         }
@@ -815,13 +847,13 @@ decode_serial_kernel(const __grid_constant__ RowParams rp, int V, int cl_log2, c
 #pragma unroll
         for (int e = 1; e < 4; e++) {
             Ce += qe[e - 1];
-            const bool oke = (eg + e < eend) & (lq::cum_of(Ce, (uint32_t)(eg + e), sc) <= target);
+            const bool oke = (eg + e < eend) & (lq::cum_of(Ce, (uint32_t)(eg + e), sc_now) <= target);
             sym = oke ? eg + e : sym;
             Cs = oke ? Ce : Cs;
             qsym = oke ? qe[e] : qsym;
         }
-        uint32_t lo = lq::cum_of(Cs, (uint32_t)sym, sc);
-        uint32_t hi = (sym == V - 1) ? 0u : lq::cum_of(Cs + qsym, (uint32_t)sym + 1, sc);
+        uint32_t lo = lq::cum_of(Cs, (uint32_t)sym, sc_now);
+        uint32_t hi = (sym == V - 1) ? 0u : lq::cum_of(Cs + qsym, (uint32_t)sym + 1, sc_now);
         sym = __shfl_sync(0xffffffffu, sym, src);
         lo = __shfl_sync(0xffffffffu, lo, src);
         hi = __shfl_sync(0xffffffffu, hi, src);
@@ -1017,7 +1049,6 @@ cudaError_t launch_decode(const float* logits, int64_t n_streams, int64_t T, int
     int cl = 1;
     const int path = path_for(logits, V, stream_stride, tok_stride, &cl);
     if (path < 0) return cudaErrorInvalidValue;
-    const int cl_log2 = log2_of(cl);
     int64_t tc = summ_chunk_rows(cl) / n_streams;
     tc = tc < 1 ? 1 : (tc > T ? T : tc);
     uint64_t* summ = nullptr;
@@ -1029,12 +1060,15 @@ cudaError_t launch_decode(const float* logits, int64_t n_streams, int64_t T, int
         const RowParams rp{logits + t0 * tok_stride, n_streams, tn, stream_stride, tok_stride, ntok, t0};
         e = launch_summary(rp, V, cl, path, summ, st);
         if (e != cudaSuccess) break;
-        if (path == 0)
-            decode_serial_kernel<1><<<serial_blocks, 128, 0, st>>>(rp, V, cl_log2, summ, state, bytes, offsets,
-                                                                    syms + t0, sym_stride, P);
-        else
-            decode_serial_kernel<4><<<serial_blocks, 128, 0, st>>>(rp, V, cl_log2, summ, state, bytes, offsets,
-                                                                    syms + t0, sym_stride, P);
+#define LAC_SERIAL(VEC_, CL_)                                                                                    \
+    decode_serial_kernel<VEC_, CL_><<<serial_blocks, 128, 0, st>>>(rp, V, summ, state, bytes, offsets, syms + t0, \
+                                                                    sym_stride, P)
+        if (path == 0) LAC_SERIAL(1, 1);
+        else if (cl == 1) LAC_SERIAL(4, 1);
+        else if (cl == 2) LAC_SERIAL(4, 2);
+        else if (cl == 4) LAC_SERIAL(4, 4);
+        else LAC_SERIAL(4, 8);
+#undef LAC_SERIAL
         e = cudaGetLastError();
     }
     const cudaError_t ef = cudaFreeAsync(summ, st);
