@@ -65,9 +65,9 @@ int lac_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *hbm_by
 int lac_cdf_build_f32(const float *d_logits, int64_t rows, int32_t vocab, int64_t row_stride,
                       uint32_t *d_cum, void *stream);
 
-/* Encode-side fused lookup: for row r and symbol d_syms[r] write d_pairs[2r] = cum[sym],
- * d_pairs[2r+1] = cum[sym+1] (0 encodes 2^32 for the last symbol).  The table itself is
- * never written to memory.  Replaces calc_dist + symbol_to_range's table reads. */
+/* Encode-side lookup: for row r and symbol d_syms[r] write d_pairs[2r] = cum[sym],
+ * d_pairs[2r+1] = cum[sym+1] (0 encodes 2^32 for the last symbol).  One HBM pass over the logits
+ * (row summaries) plus one warp per row; the table itself is never written to memory.  Replaces calc_dist + symbol_to_range's table reads. */
 int lac_cdf_lookup_f32(const float *d_logits, int64_t rows, int32_t vocab, int64_t row_stride,
                        const int32_t *d_syms, uint32_t *d_pairs, uint32_t *d_status, void *stream);
 
@@ -112,9 +112,9 @@ int lac_ac_encode_pairs(const uint32_t *d_pairs, int64_t n_streams, int64_t T, i
                         int64_t tok_stride, const int32_t *d_ntok, lac_enc_state *d_state,
                         uint8_t *d_out, int64_t out_stride, int finish, int prec, void *stream);
 
-/* Fused decode: for every stream, T sequential tokens; token t of stream s reads the logits
- * row at d_logits + s * stream_stride + t * tok_stride (elements), rebuilds the LQ32 CDF on
- * chip, finds the symbol containing the code value (val_to_symbol), narrows (l, h) and
+/* Decode (one HBM pass over the logits for the row summaries, then one warp per stream): for every
+ * stream, T sequential tokens; token t of stream s reads the logits row at
+ * d_logits + s * stream_stride + t * tok_stride (elements), rebuilds the LQ32 CDF on chip, finds the symbol containing the code value (val_to_symbol), narrows (l, h) and
  * renormalises from the stream's bits.  Symbols go to d_syms[s * sym_stride + t].
  * T = 1 is the model-in-the-loop step. */
 int lac_ac_decode_logits_f32(const float *d_logits, int64_t n_streams, int64_t T, int64_t stream_stride,

@@ -1,8 +1,12 @@
-// cdf_kernels.cu -- fused logits -> LQ32 CDF kernels (north-star part (a)) and the decoder side of
-// part (b): a bandwidth-bound row-summary pass plus a latency-bound serial pass per stream.
+// cdf_kernels.cu -- logits -> LQ32 CDF kernels (north-star part (a)) and the decoder side of part (b).
 //
-// One persistent CTA of 1024 threads per SM walks its rows.  Warp w owns a contiguous
-// segment of the row; the row is read from HBM exactly once and then lives in registers:
+// Both directions are ONE bandwidth-bound pass over the logits plus small dependent passes:
+//
+//   encode:  summary_kernel -> pair_kernel (1 warp / row)             -> encode_pairs_kernel (coder_kernels.cu)
+//   decode:  summary_kernel -> decode_serial_kernel (1 warp / stream, walks its tokens)
+//
+// summary_kernel: one persistent CTA of 1024 threads per SM walks its rows.  Warp w owns a contiguous segment
+// of the row; the row is read from HBM exactly once and then lives in registers:
 //
 //   staging  the row arrives as NCH TMA bulk copies (cp.async.bulk; 2 x 64 KB by default) into a
 //            shared-memory ring, each chunk with its own mbarrier.  As soon as the warps of a chunk
@@ -10,18 +14,14 @@
 //            chunk of the CTA's NEXT row, so 128 KB per SM stay in flight during the compute phases.
 //   phase A  row max                      (REDUX + the one block barrier of the row)
 //   phase B  q_i with packed fp32x2 math (FADD2 / FFMA2), exact integer sums (lane -> warp)
-//   finish   the LAST warp to finish phase B (shared-memory atomic counter) does the row-level
-//            bookkeeping once -- prefix of the 32 warp totals, the scale (one division), for decode
-//            the owner warp -- and arrives on the `done` mbarrier; there is no second block barrier.
-//   final    LOOKUP: only the warp that owns the coded symbol waits for `done`; it writes
-//                    cum[sym], cum[sym+1] from masked integer sums (no table is written); the other
-//                    31 warps are already draining the next row.
-//            BUILD : whole table via in-warp exclusive scans.
-//            SUMMARY (decode, pass 1): the finishing warp writes the row's reference, scale and the 32 * CL
-//                    warp-segment prefixes (272 bytes per 32000-element row); nobody waits for anything.
-//            DECODE  (pass 2, decode_serial_kernel): one warp per stream walks its tokens: probe -> segment
-//                    from the summary -> re-read that one segment (<= 4 KB) -> q -> symbol -> A_from_bin update.
-// The integer formulation (lq32.cuh) makes the result independent of this decomposition.
+//   finish   the LAST warp to finish phase B (shared-memory atomic counter) scans the 32 warp totals and writes
+//            the row summary {nref, total[CL], prefix[CL][32]} (272 bytes per 32000-element row); no division,
+//            no table, nobody waits for it.  (build_kernel, the full-table variant, also derives the scale and
+//            publishes it through the `done` mbarrier.)
+//
+// The second passes work from the summary and re-read only the one warp segment (<= 4 KB) they need; q is a
+// function of (x, nref) only (lq32.cuh), so the recomputed values are bit-identical to pass 1 and the result does
+// not depend on the decomposition.
 #include <climits>
 #include <cstdint>
 #include <cstdlib>
