@@ -1004,7 +1004,11 @@ static cudaError_t summ_alloc(uint64_t** summ, int64_t rows, int cl, cudaStream_
     }
     return cudaMallocAsync(reinterpret_cast<void**>(summ), (size_t)(rows * summ_words(cl) * 8), st);
 }
-static int64_t summ_chunk_rows(int cl) { return (64ll << 20) / (summ_words(cl) * 8); }
+static int64_t summ_chunk_rows(int cl) {  // LAC_SUMMARY_BYTES: test switch, forces many small chunks
+    static const int64_t budget = getenv("LAC_SUMMARY_BYTES") ? atoll(getenv("LAC_SUMMARY_BYTES")) : (64ll << 20);
+    const int64_t rows = budget / (summ_words(cl) * 8);
+    return rows < 1 ? 1 : rows;
+}
 static int log2_of(int cl) {
     int l = 0;
     while ((1 << l) < cl) l++;

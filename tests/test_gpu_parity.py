@@ -405,3 +405,50 @@ def test_host_buffer_api_roundtrip():
         assert out[s, :nbytes[s]].tobytes() == _oracle_stream(logits[s], syms[s], 48)
     back = coder.decode_logits_host(logits, data, offs)
     assert np.array_equal(back, syms)
+
+
+_CHUNK_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+from lac_b200 import coder
+rng = np.random.default_rng(11)
+out = {}
+for V, S, T in ((1000, 5, 37), (40000, 3, 9)):
+    logits = (rng.standard_normal((S, T, V)) * 4).astype(np.float32)
+    syms = rng.integers(0, V, (S, T)).astype(np.int32)
+    ntok = rng.integers(0, T + 1, S).astype(np.int32)
+    ntok[0] = T
+    dl, ds, dn = (torch.from_numpy(a).cuda() for a in (logits, syms, ntok))
+    enc = coder.StreamEncoder(S, capacity_bytes=T * 8 + 64)
+    enc.encode_logits(dl, ds, ntok=dn, finish=True)
+    streams, _ = enc.bitstreams()
+    dec = coder.StreamDecoder(streams).decode_logits(dl, ntok=dn).cpu().numpy()
+    for s in range(S):
+        assert np.array_equal(dec[s, :ntok[s]], syms[s, :ntok[s]]), (V, s)
+    out[str(V)] = np.frombuffer(b"".join(streams), dtype=np.uint8)
+np.savez(sys.argv[2], **out)
+"""
+
+
+@pytest.mark.gpu
+def test_row_and_token_chunking_of_the_summary_scratch(tmp_path):
+    """lac_cdf_lookup_f32 / lac_ac_decode_logits_f32 process long inputs in chunks of rows / tokens bounded by the
+    summary scratch size; with a 4 KB budget every call runs many chunks (ragged streams included) and must
+    produce the same bytes and symbols as the unchunked run."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for name, budget in (("full", None), ("tiny", "4096")):
+        env = dict(os.environ)
+        env.pop("LAC_SUMMARY_BYTES", None)
+        if budget:
+            env["LAC_SUMMARY_BYTES"] = budget
+        out = tmp_path / f"{name}.npz"
+        r = subprocess.run([sys.executable, "-c", _CHUNK_SCRIPT, root, str(out)], env=env, capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[name] = np.load(out)
+    for k in res["full"].files:
+        assert np.array_equal(res["full"][k], res["tiny"][k])
