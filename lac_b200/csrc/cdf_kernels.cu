@@ -371,16 +371,34 @@ struct RowEngine {
             const int gb = gbeg(V), ge = gend(V), ln = lane();
             if (TMA) {
                 if (cbytes(V)) mbar_wait(&g_ctl.full[chunk()], it & 1);
-                const unsigned char* sl = slot() - (size_t)cg0(V) * 16;
+                const unsigned char* sl = slot() + (size_t)(gb + ln - cg0(V)) * 16;
+                if (ge - gb > (IT - 1) * 32) {
+                    // the usual shape (a warp segment longer than 7 slabs): slabs 0..6 are complete for every lane,
+                    // no -inf initialisation and no predicates there (32 instructions per thread and row less)
 #pragma unroll
-                for (int k = 0; k < IT; k++) {
-                    int g = gb + k * 32 + ln;
+                    for (int k = 0; k < IT - 1; k++) {
+                        const float4 v = *reinterpret_cast<const float4*>(sl + k * 512);
+                        x[4 * k + 0] = v.x;
+                        x[4 * k + 1] = v.y;
+                        x[4 * k + 2] = v.z;
+                        x[4 * k + 3] = v.w;
+                    }
                     float4 v = make_float4(lq::neg_inf(), lq::neg_inf(), lq::neg_inf(), lq::neg_inf());
-                    if (g < ge) v = *reinterpret_cast<const float4*>(sl + (size_t)g * 16);
-                    x[4 * k + 0] = v.x;
-                    x[4 * k + 1] = v.y;
-                    x[4 * k + 2] = v.z;
-                    x[4 * k + 3] = v.w;
+                    if (gb + (IT - 1) * 32 + ln < ge) v = *reinterpret_cast<const float4*>(sl + (IT - 1) * 512);
+                    x[4 * (IT - 1) + 0] = v.x;
+                    x[4 * (IT - 1) + 1] = v.y;
+                    x[4 * (IT - 1) + 2] = v.z;
+                    x[4 * (IT - 1) + 3] = v.w;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < IT; k++) {
+                        float4 v = make_float4(lq::neg_inf(), lq::neg_inf(), lq::neg_inf(), lq::neg_inf());
+                        if (gb + k * 32 + ln < ge) v = *reinterpret_cast<const float4*>(sl + k * 512);
+                        x[4 * k + 0] = v.x;
+                        x[4 * k + 1] = v.y;
+                        x[4 * k + 2] = v.z;
+                        x[4 * k + 3] = v.w;
+                    }
                 }
             } else {
 #pragma unroll
