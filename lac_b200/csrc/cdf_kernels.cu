@@ -364,8 +364,11 @@ struct RowEngine {
     // row has left shared memory.  On return q[] holds this thread's q values; the row-level results
     // (g_ctl.pref, Q, R, s) are valid once wait_done() returns.  summ != nullptr: the finishing warp also writes
     // the row summary (reference, scale, warp-segment prefixes) there.
-    __device__ __forceinline__ void reduce(const float* __restrict__ row, const float* next_row, int V,
-                                           uint32_t (&q)[kPerThread], uint64_t* summ = nullptr) {
+    // next_row() and summ() are evaluated lazily, by the chunk leaders resp. the finishing warp only: pointer
+    // arithmetic every thread would otherwise redo per row costs issue slots the row loop does not have.
+    template <class NextFn, class SummFn>
+    __device__ __forceinline__ void reduce(const float* __restrict__ row, NextFn next_row, int V,
+                                           uint32_t (&q)[kPerThread], SummFn summ) {
         float x[kPerThread];
         {
             const int gb = gbeg(V), ge = gend(V), ln = lane();
@@ -425,9 +428,12 @@ struct RowEngine {
             // m depends on every shared-memory load of this thread, so after this barrier the chunk is
             // fully in registers and the slot can be overwritten by the next row
             named_bar_sync(1 + chunk(), 32 * kWarpsPerChunk);
-            if (next_row) {
-                if (leader()) fence_proxy_async();
-                issue(next_row, V);
+            if (leader()) {
+                const float* nr = next_row();
+                if (nr) {
+                    fence_proxy_async();
+                    issue(nr, V);
+                }
             }
         }
         const int mw = __reduce_max_sync(0xffffffffu, f2ord(m));
@@ -479,10 +485,11 @@ struct RowEngine {
         if (lane() == 0) {
             g_ctl.wsum[warp()] = ws;
             fence_acq_rel_cta();
-            prev = atomicAdd(&g_ctl.arrive, 1u);
+            // (plain PTX: atomicAdd() under a lane test is compiled into a warp-aggregation sequence)
+            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(prev) : "r"(smem_u32(&g_ctl.arrive)) : "memory");
         }
         prev = __shfl_sync(0xffffffffu, prev, 0);
-        if (prev == kWarps - 1) finish_row(V, par, (it >> 1) & 1, summ, nrow_u);  // last warp of the row: every wsum[] is visible
+        if (prev == kWarps - 1) finish_row(V, par, (it >> 1) & 1, summ(), nrow_u);  // last warp of the row: every wsum[] is visible
         it++;
     }
 
@@ -633,7 +640,8 @@ build_kernel(const __grid_constant__ RowParams rp, int V, uint32_t* __restrict__
         const float* row = seq.ptr(rp);
         seq.next(rp, stride);
         uint32_t q[kPerThread];
-        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, V, q);
+        eng.reduce(row, [&] { return seq.valid(rp) ? seq.ptr(rp) : nullptr; }, V, q,
+                   [] { return static_cast<uint64_t*>(nullptr); });
         const int warp = Eng::warp(), lane = Eng::lane(), gbeg = Eng::gbeg(V), gend = Eng::gend(V);
         eng.wait_done();
         uint64_t base = ctl.pref[warp];
@@ -706,11 +714,12 @@ summary_kernel(const __grid_constant__ RowParams rp, int V, uint64_t* __restrict
     seq.init(rp, Clu<CL>::id(), Clu<CL>::count());
     if (seq.valid(rp)) Eng::issue(seq.ptr(rp), V);
     while (seq.valid(rp)) {
-        uint64_t* out = summ + seq.index(rp) * summ_words(CL);
+        const int64_t idx = seq.index(rp);
         const float* row = seq.ptr(rp);
         seq.next(rp);
         uint32_t q[kPerThread];
-        eng.reduce(row, seq.valid(rp) ? seq.ptr(rp) : nullptr, V, q, out);
+        eng.reduce(row, [&] { return seq.valid(rp) ? seq.ptr(rp) : nullptr; }, V, q,
+                   [&] { return summ + idx * summ_words(CL); });
     }
     Eng::teardown();
 }
