@@ -424,23 +424,20 @@ struct RowEngine {
         float m = lq::neg_inf();
 #pragma unroll
         for (int i = 0; i < kPerThread; i++) m = fmaxf(m, x[i]);
-        if (TMA) {
-            // m depends on every shared-memory load of this thread, so after this barrier the chunk is
-            // fully in registers and the slot can be overwritten by the next row
-            named_bar_sync(1 + chunk(), 32 * kWarpsPerChunk);
-            if (leader()) {
-                const float* nr = next_row();
-                if (nr) {
-                    fence_proxy_async();
-                    issue(nr, V);
-                }
-            }
-        }
         const int mw = __reduce_max_sync(0xffffffffu, f2ord(m));
         const uint32_t par = it & 1;
         int* red = g_ctl.red_max[par];
         if (lane() == 0) red[warp()] = mw;
-        __syncthreads();  // the only block-wide barrier of the row
+        __syncthreads();  // the only barrier of the row
+        if (TMA && leader()) {
+            // m depends on every shared-memory load of a thread, so after the barrier the row is fully in
+            // registers and both slots can be overwritten by the next row
+            const float* nr = next_row();
+            if (nr) {
+                fence_proxy_async();
+                issue(nr, V);
+            }
+        }
         int mx = __reduce_max_sync(0xffffffffu, red[lane()]);
         if (CL > 1 && threadIdx.x < CL) {  // send this CTA's maximum to every CTA of the cluster (incl. itself)
             if (threadIdx.x == 0) mbar_expect_tx(&g_ctl.cl_max_bar[par], CL * 4);
