@@ -592,22 +592,33 @@ pair_kernel(const float* __restrict__ logits, int64_t rows, int64_t row_stride, 
     const float* row = logits + r * row_stride;
     uint64_t part = 0;
     uint32_t qs = 0;
-    for (int g = seg(gw) + lane; g <= gs; g += 32) {  // groups in front of (and including) the symbol's group
-        if (VEC == 4) {
-            const float4 x = __ldg(reinterpret_cast<const float4*>(row) + g);
-            const uint32_t q0 = lq::q_of(x.x, nref), q1 = lq::q_of(x.y, nref), q2 = lq::q_of(x.z, nref),
-                           q3 = lq::q_of(x.w, nref);
-            if (g < gs) {
-                part += (uint64_t)((q0 + q1) + (q2 + q3));
-            } else {
-                const int es = sym & 3;
-                part += (uint64_t)(es > 0 ? q0 : 0u) + (es > 1 ? q1 : 0u) + (es > 2 ? q2 : 0u);
-                qs = es == 0 ? q0 : es == 1 ? q1 : es == 2 ? q2 : q3;
-            }
-        } else {
-            const uint32_t q0 = lq::q_of(__ldg(row + g), nref);
-            if (g < gs) part += q0;
-            else qs = q0;
+    // groups in front of (and including) the symbol's group: at most 8 per lane, all loads issued together from
+    // addresses clamped to the symbol's group, masked afterwards
+    const int g0 = seg(gw) + lane;
+    if (VEC == 4) {
+        float4 x[kPerThread / 4];
+#pragma unroll
+        for (int k = 0; k < kPerThread / 4; k++) x[k] = __ldg(reinterpret_cast<const float4*>(row) + min(g0 + 32 * k, gs));
+#pragma unroll
+        for (int k = 0; k < kPerThread / 4; k++) {
+            const int g = g0 + 32 * k;
+            uint32_t q0, q1, q2, q3;
+            q_of2(x[k].x, x[k].y, (uint32_t)nref, q0, q1);
+            q_of2(x[k].z, x[k].w, (uint32_t)nref, q2, q3);
+            const int es = g < gs ? 4 : (g == gs ? (sym & 3) : -1);  // elements of this group in front of the symbol
+            part += (uint64_t)(es > 0 ? q0 : 0u) + (es > 1 ? q1 : 0u) + (uint64_t)(es > 2 ? q2 : 0u) + (es > 3 ? q3 : 0u);
+            if (g == gs) qs = es == 0 ? q0 : es == 1 ? q1 : es == 2 ? q2 : q3;
+        }
+    } else {
+        float x[kPerThread];
+#pragma unroll
+        for (int k = 0; k < kPerThread; k++) x[k] = __ldg(row + min(g0 + 32 * k, gs));
+#pragma unroll
+        for (int k = 0; k < kPerThread; k++) {
+            const int g = g0 + 32 * k;
+            const uint32_t q0 = lq::q_of(x[k], nref);
+            part += g < gs ? q0 : 0u;
+            if (g == gs) qs = q0;
         }
     }
     part = warp_sum48(part);

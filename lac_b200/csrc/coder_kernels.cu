@@ -57,16 +57,31 @@ __global__ void encode_pairs_kernel(const uint2* __restrict__ pairs, int64_t n_s
     bw.status = state[s].status;
     const int64_t Ts = ntok ? (int64_t)ntok[s] : T;
     const uint2* p = pairs + s * stream_stride;
-    for (int64_t t = 0; t < Ts; t++) {
-        uint2 pr = p[t * tok_stride];
-        if (pr.y != 0 && pr.y <= pr.x) {  // zero-width symbol: the reference would never terminate
-            bw.status |= LAC_ST_TABLE;
-            break;
+    // the pairs of a stream are T * 8 bytes apart from the next stream's, so every load is its own memory
+    // transaction: fetch them eight tokens at a time (independent loads in flight together), then code serially
+    constexpr int kBatch = 8;
+    bool bad = false;
+    for (int64_t t0 = 0; t0 < Ts && !bad; t0 += kBatch) {
+        uint2 pr[kBatch];
+#pragma unroll
+        for (int j = 0; j < kBatch; j++) {
+            const int64_t t = t0 + j < Ts ? t0 + j : Ts - 1;
+            pr[j] = p[t * tok_stride];
         }
-        coder::ac_narrow32(l, h, pr.x, pr.y);
-        int k = coder::renorm_count((uint64_t)(h - l + 1), P);
-        int64_t E = coder::renorm_apply(l, h, P, k);
-        bw.append(E, k);
+#pragma unroll
+        for (int j = 0; j < kBatch; j++) {
+            if (t0 + j < Ts && !bad) {
+                if (pr[j].y != 0 && pr[j].y <= pr[j].x) {  // zero-width symbol: the reference would never terminate
+                    bw.status |= LAC_ST_TABLE;
+                    bad = true;
+                } else {
+                    coder::ac_narrow32(l, h, pr[j].x, pr[j].y);
+                    int k = coder::renorm_count((uint64_t)(h - l + 1), P);
+                    int64_t E = coder::renorm_apply(l, h, P, k);
+                    bw.append(E, k);
+                }
+            }
+        }
     }
     if (finish && !(bw.status & LAC_ST_TABLE)) coder::ac_flush(l, h, P, bw);
     bw.close();
