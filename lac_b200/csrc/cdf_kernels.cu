@@ -444,38 +444,21 @@ struct RowEngine {
             st_async_u32(mapa(smem_u32(&g_ctl.cl_max[par][Clu<CL>::rank()]), threadIdx.x), (uint32_t)mx,
                          mapa(smem_u32(&g_ctl.cl_max_bar[par]), threadIdx.x));
         }
-        // phase B: q against the reference of THIS CTA's maximum, uint32 sums per 4 elements (4 q < 2^31.5).
-        // (a degenerate reference -- no finite maximum, +inf, out of range -- pushes every shift count past 31,
-        // i.e. q = 0 everywhere, without a second code path)
-        const int nloc = lq::ref_of_max(ord2f(mx));
-        const uint32_t nref_u = lq::ref_valid(nloc) ? (uint32_t)nloc : 0xFFFFFFFFu;
-        uint32_t nrow_u = nref_u;  // reference of the whole row (differs from nref_u only in a cluster)
-        uint64_t lane_sum = 0;
-        if (CL == 1) {
-#pragma unroll
-            for (int i = 0; i < kPerThread; i += 4) {
-                q_of2(x[i], x[i + 1], nref_u, q[i], q[i + 1]);
-                q_of2(x[i + 2], x[i + 3], nref_u, q[i + 2], q[i + 3]);
-                lane_sum += (q[i] + q[i + 1]) + (q[i + 2] + q[i + 3]);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < kPerThread; i += 2) q_of2(x[i], x[i + 1], nref_u, q[i], q[i + 1]);
-            // The other CTAs' maxima arrived while phase B ran.  q against the row-wide reference is the local
-            // q shifted by the distance of the two references: floor(floor(a / 2^j) / 2^k) = floor(a / 2^(j+k)).
+        // phase B against the row-wide reference (in a cluster: after the peers' maxima have arrived)
+        if (CL > 1) {
             mbar_wait_peers(&g_ctl.cl_max_bar[par], (it >> 1) & 1);
 #pragma unroll
             for (int p = 0; p < CL; p++) mx = max(mx, g_ctl.cl_max[par][p]);
-            const int nref = lq::ref_of_max(ord2f(mx));
-            uint32_t delta = (uint32_t)nref - (uint32_t)nloc;
-            delta = (lq::ref_valid(nref) && delta < 32u) ? delta : 32u;
-            nrow_u = lq::ref_valid(nref) ? (uint32_t)nref : 0xFFFFFFFFu;
+        }
+        const int nloc = lq::ref_of_max(ord2f(mx));
+        const uint32_t nref_u = lq::ref_valid(nloc) ? (uint32_t)nloc : 0xFFFFFFFFu;
+        const uint32_t nrow_u = nref_u;
+        uint64_t lane_sum = 0;
 #pragma unroll
-            for (int i = 0; i < kPerThread; i += 4) {
-#pragma unroll
-                for (int e = 0; e < 4; e++) q[i + e] = __funnelshift_rc(q[i + e], 0u, delta);
-                lane_sum += (q[i] + q[i + 1]) + (q[i + 2] + q[i + 3]);
-            }
+        for (int i = 0; i < kPerThread; i += 4) {
+            q_of2(x[i], x[i + 1], nref_u, q[i], q[i + 1]);
+            q_of2(x[i + 2], x[i + 3], nref_u, q[i + 2], q[i + 3]);
+            lane_sum += (q[i] + q[i + 1]) + (q[i + 2] + q[i + 3]);
         }
         const uint64_t ws = warp_sum48(lane_sum);
         uint32_t prev = 0;
