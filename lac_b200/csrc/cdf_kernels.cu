@@ -9,10 +9,10 @@
 // of the row; the row is read from HBM exactly once and then lives in registers:
 //
 //   staging  the row arrives as NCH TMA bulk copies (cp.async.bulk; 2 x 64 KB by default) into a
-//            shared-memory ring, each chunk with its own mbarrier.  As soon as the warps of a chunk
-//            have moved it to registers they re-arm the barrier and issue the bulk copy of the SAME
-//            chunk of the CTA's NEXT row, so 128 KB per SM stay in flight during the compute phases.
-//   phase A  row max                      (REDUX + the one block barrier of the row)
+//            shared-memory ring, each chunk with its own mbarrier; the warps of a chunk move it to registers.
+//   phase A  row max (REDUX + the ONE barrier of the row).  Right after it the chunk leaders re-arm their
+//            mbarriers and issue the bulk copies of the CTA's NEXT row, so 128 KB per SM are in flight
+//            during the compute phase.  In a cluster the CTA maxima then cross DSMEM (st.async).
 //   phase B  q_i with packed fp32x2 math (FADD2 / FFMA2), exact integer sums (lane -> warp)
 //   finish   the LAST warp to finish phase B (shared-memory atomic counter) scans the 32 warp totals and writes
 //            the row summary {nref, total[CL], prefix[CL][32]} (272 bytes per 32000-element row); no division,
@@ -89,7 +89,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_acq_rel_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
     float4 v;
