@@ -452,3 +452,42 @@ def test_row_and_token_chunking_of_the_summary_scratch(tmp_path):
         res[name] = np.load(out)
     for k in res["full"].files:
         assert np.array_equal(res["full"][k], res["tiny"][k])
+
+
+_PATH_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+from lac_b200 import coder
+from oracle import oracle as orc
+rng = np.random.default_rng(21)
+for V, S, T in ((32000, 6, 5), (4096, 9, 7), (1000, 4, 6)):
+    logits = (rng.standard_normal((S, T, V)) * 5).astype(np.float32)
+    syms = rng.integers(0, V, (S, T)).astype(np.int32)
+    dl, ds = torch.from_numpy(logits).cuda(), torch.from_numpy(syms).cuda()
+    cum = coder.cdf_build(dl.view(S * T, V)).cpu().numpy().view(np.uint32)
+    assert np.array_equal(cum, orc.lq32_cdf(logits.reshape(S * T, V))), V
+    enc = coder.StreamEncoder(S, capacity_bytes=T * 8 + 64)
+    enc.encode_logits(dl, ds, finish=True)
+    streams, _ = enc.bitstreams()
+    lo, hi = orc.lq32_lookup(logits[0], syms[0])
+    assert streams[0] == orc.pack_bits(orc.ac_encode_pairs(lo, hi, prec=48)).tobytes(), V
+    assert np.array_equal(coder.StreamDecoder(streams).decode_logits(dl).cpu().numpy(), syms), V
+print("ok")
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"LAC_NO_TMA": "1"}, {"LAC_TMA_CHUNKS": "4"}, {"LAC_TMA_CHUNKS": "8"}])
+def test_alternative_staging_paths_are_bit_exact(env):
+    """The measurement switches select other instantiations of the row engine (128-bit LDG staging, 4 or 8 TMA
+    chunks per row); they must stay bit-exact with the oracle like the default 2 x 64 KB TMA path."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    for k in ("LAC_NO_TMA", "LAC_TMA_CHUNKS"):
+        e.pop(k, None)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-c", _PATH_SCRIPT, root], env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
