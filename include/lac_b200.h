@@ -123,6 +123,20 @@ int lac_ac_decode_logits_f32(const float *d_logits, int64_t n_streams, int64_t T
                              int32_t *d_syms, int64_t sym_stride, int prec, void *stream);
 
 /* ------------------------------------------------------------------------------------
+ * The reference's uniform base class Predictor(n) (arith_code.py:63-74): symbol s of n maps to
+ * [floor(s w / n), floor((s + 1) w / n)).  AC() without arguments is AC(Predictor(3), 16).
+ * Symbols int32 at d_syms[s * sym_stride + t]; everything else as for the pair / table coders.
+ * Streams whose interval is narrower than n symbols set LAC_ST_TABLE (the reference never
+ * terminates there); decode returns the symbol whose range holds the code value.
+ * ---------------------------------------------------------------------------------- */
+int lac_ac_encode_uniform(const int32_t *d_syms, int64_t n_streams, int64_t T, int64_t sym_stride,
+                          const int32_t *d_ntok, int32_t n_symbols, lac_enc_state *d_state,
+                          uint8_t *d_out, int64_t out_stride, int finish, int prec, void *stream);
+int lac_ac_decode_uniform(int64_t n_streams, int64_t T, const int32_t *d_ntok, int32_t n_symbols,
+                          lac_dec_state *d_state, const uint8_t *d_bytes, const int64_t *d_offsets,
+                          int32_t *d_syms, int64_t sym_stride, int prec, void *stream);
+
+/* ------------------------------------------------------------------------------------
  * General integer tables ("given identical integer frequency tables the bitstream is
  * bit-exact with the reference coder"): int64 inclusive cumulative tables exactly as
  * CDFPredictor.dist holds them, any total < 2^63, including the fudged_dist rescale

@@ -49,6 +49,8 @@ SIGNATURES = {
     "lac_enc_init": [_p, _i64, _int, _p],
     "lac_dec_init": [_p, _i64, _int, _p, _p, _p],
     "lac_ac_encode_pairs": [_p, _i64, _i64, _i64, _i64, _p, _p, _p, _i64, _int, _int, _p],
+    "lac_ac_encode_uniform": [_p, _i64, _i64, _i64, _p, _i32, _p, _p, _i64, _int, _int, _p],
+    "lac_ac_decode_uniform": [_i64, _i64, _p, _i32, _p, _p, _p, _p, _i64, _int, _p],
     "lac_ac_decode_logits_f32": [_p, _i64, _i64, _i64, _i64, _i32, _p, _p, _p, _p, _p, _i64, _int, _p],
     "lac_ac_encode_tables": [_p, _i32, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _i64, _int, _int, _int, _p],
     "lac_ac_decode_tables": [_p, _i32, _i64, _i64, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i64, _int, _int, _p],

@@ -8,6 +8,9 @@ What maps to what (pramasoul/lac arith_code.py):
     A_from_bin.run / decode                    :233-345  -> lac_ac_decode_tables
     group_bits / ungroup_bits                  :347-362  byte layout of every stream
 
+The uniform base class Predictor(n) (floor-mapped ranges, the default AC() = AC(Predictor(3), 16)) goes through
+lac_ac_encode_uniform / lac_ac_decode_uniform and is bit-exact with the reference as well.
+
 Differences that cannot be avoided, both documented in DESIGN.md:
   * the reference decoder has no length framing (it emits symbols while its bit window allows and
     then guesses in flush()); here run()/decode() take the number of symbols to produce;
@@ -25,20 +28,18 @@ import numpy as np
 
 # ------------------------------------------------------------------ predictors (table providers)
 class Predictor:
-    """Uniform predictor over n symbols (arith_code.py:63-74), expressed as a table so the GPU coder
-    can use it.  NOTE: the reference's uniform Predictor maps ranges with floor; as a CDFPredictor
-    table it is coded with ceil like every other table (out of scope)."""
+    """Uniform predictor over n symbols (arith_code.py:63-74): symbol s maps to
+    [floor(s w / n), floor((s + 1) w / n)).  Coded by the dedicated uniform kernels, bit-exact with the reference
+    (tests/golden/ac_uniform.npz)."""
 
     def __init__(self, n: int):
         self.n = n
 
-    @property
-    def dist(self):
-        return list(range(1, self.n + 1))
+    def val_to_symbol(self, v, denom):
+        return (v * self.n) // denom
 
-    @property
-    def minp(self):
-        return 1
+    def symbol_to_range(self, s, denom):
+        return (s * denom) // self.n, ((s + 1) * denom) // self.n
 
     def accept(self, symbol):
         pass
@@ -142,8 +143,11 @@ def _bits_of(data: bytes, nbits: int) -> List[int]:
 
 
 # ------------------------------------------------------------------ the coder pair
+ternary = Predictor(3)  # arith_code.py:143
+
+
 class AC:
-    def __init__(self, predictor, prec: int = 16, wrap64: bool = False):
+    def __init__(self, predictor=ternary, prec: int = 16, wrap64: bool = False):
         self.predictor = predictor
         self.precision = prec
         self.wrap64 = wrap64  # reproduce Llama_AC's numpy-int64 overflow in fudged_dist (llama_compress.py:29)
@@ -173,12 +177,17 @@ class A_to_bin:
         import torch
         from . import coder
         symbols = [int(s) for s in symbols]
-        dist, minp = materialise_tables(self.predictor, symbols)
         T = len(symbols)
         enc = coder.StreamEncoder(1, prec=self.precision, capacity_bytes=T * 8 + 64)
+        uniform = type(self.predictor) is Predictor
+        if not uniform:
+            dist, minp = materialise_tables(self.predictor, symbols)
         if T == 0:
             if stop:
                 enc.finish()
+        elif uniform:
+            enc.encode_uniform(torch.tensor([symbols], dtype=torch.int32, device="cuda"), self.predictor.n,
+                               finish=bool(stop))
         else:
             enc.encode_tables(torch.from_numpy(dist).cuda(), torch.tensor([symbols], dtype=torch.int32, device="cuda"),
                               torch.from_numpy(minp).cuda(), finish=bool(stop), wrap64=self.wrap64)
@@ -213,6 +222,8 @@ class A_from_bin:
         import torch
         from . import coder
         dec = coder.StreamDecoder([bytes(data)], prec=self.precision)
+        if type(self.predictor) is Predictor:
+            return dec.decode_uniform(self.predictor.n, count).cpu().numpy()[0].astype(int).tolist()
         out: List[int] = []
         static = not hasattr(self.predictor, "dcache") or type(self.predictor).accept is Predictor.accept
         if static:  # fixed table: one GPU call for all symbols

@@ -142,6 +142,16 @@ class StreamEncoder:
                                          int(finish), self.prec, _ffi.LAC_F_WRAP64 if wrap64 else 0, _cur_stream()))
         self.finished = self.finished or finish
 
+    def encode_uniform(self, syms: torch.Tensor, n_symbols: int, ntok: Optional[torch.Tensor] = None,
+                       finish: bool = False):
+        """The reference's uniform base class Predictor(n) (arith_code.py:63-74, floor-mapped ranges)."""
+        _need_cuda(syms, "syms", torch.int32)
+        S, T = syms.shape
+        check(lib().lac_ac_encode_uniform(syms.data_ptr(), S, T, T, self._ntok(ntok), int(n_symbols),
+                                          self.state.data_ptr(), self.out.data_ptr(), self.cap, int(finish),
+                                          self.prec, _cur_stream()))
+        self.finished = self.finished or finish
+
     def acs_encode_tables(self, cdf: torch.Tensor, syms: torch.Tensor, ntok: Optional[torch.Tensor] = None,
                           finish=False):
         """ACSampler semantics (arithmetic_coding.py:73-93): int64-carried uint64 inclusive tables.
@@ -243,6 +253,15 @@ class StreamDecoder:
                                          ntok.data_ptr() if ntok is not None else None, self.state.data_ptr(),
                                          self.bytes.data_ptr(), self.offsets.data_ptr(), syms.data_ptr(), T,
                                          self.prec, _ffi.LAC_F_WRAP64 if wrap64 else 0, _cur_stream()))
+        self._check_status()
+        return syms
+
+    def decode_uniform(self, n_symbols: int, T: int, ntok: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Decoder for encode_uniform streams: the symbol whose floor-mapped range holds the code value."""
+        syms = torch.zeros((self.n, T), dtype=torch.int32, device=self.device)
+        check(lib().lac_ac_decode_uniform(self.n, T, ntok.data_ptr() if ntok is not None else None, int(n_symbols),
+                                          self.state.data_ptr(), self.bytes.data_ptr(), self.offsets.data_ptr(),
+                                          syms.data_ptr(), T, self.prec, _cur_stream()))
         self._check_status()
         return syms
 

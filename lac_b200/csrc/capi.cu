@@ -13,6 +13,10 @@
 namespace lac {
 cudaError_t launch_lookup(const float*, int64_t, int, int64_t, const int32_t*, uint32_t*, uint32_t*, cudaStream_t);
 cudaError_t launch_build(const float*, int64_t, int, int64_t, uint32_t*, cudaStream_t);
+cudaError_t launch_uniform_encode(const int32_t*, int64_t, int64_t, int64_t, const int32_t*, int, lac_enc_state*, uint8_t*,
+                                  int64_t, int, int, cudaStream_t);
+cudaError_t launch_uniform_decode(int64_t, int64_t, const int32_t*, int, lac_dec_state*, const uint8_t*, const int64_t*,
+                                  int32_t*, int64_t, int, cudaStream_t);
 cudaError_t launch_decode(const float*, int64_t, int64_t, int64_t, int64_t, int, const int32_t*, lac_dec_state*,
                           const uint8_t*, const int64_t*, int32_t*, int64_t, int, cudaStream_t);
 cudaError_t launch_dec_init(lac_dec_state*, int64_t, int, const uint8_t*, const int64_t*, cudaStream_t);
@@ -146,6 +150,30 @@ int lac_ac_decode_logits_f32(const float* d_logits, int64_t n_streams, int64_t T
     CK(lac::launch_decode(d_logits, n_streams, T, stream_stride, tok_stride, vocab, d_ntok, d_state, d_bytes,
                           d_offsets, d_syms, sym_stride, prec, (cudaStream_t)stream),
        "lac_ac_decode_logits_f32");
+    return LAC_OK;
+}
+
+int lac_ac_encode_uniform(const int32_t* d_syms, int64_t n_streams, int64_t T, int64_t sym_stride,
+                          const int32_t* d_ntok, int32_t n_symbols, lac_enc_state* d_state, uint8_t* d_out,
+                          int64_t out_stride, int finish, int prec, void* stream) {
+    if ((!d_syms && T > 0) || !d_state || !d_out || n_streams < 0 || T < 0 || out_stride < 1 || n_symbols < 1)
+        return fail(LAC_E_ARG, "lac_ac_encode_uniform: bad argument");
+    if (!prec_ok(prec, 2)) return fail(LAC_E_ARG, "lac_ac_encode_uniform: prec %d outside [2, 60]", prec);
+    CK(lac::launch_uniform_encode(d_syms, n_streams, T, sym_stride, d_ntok, n_symbols, d_state, d_out, out_stride,
+                                  finish, prec, (cudaStream_t)stream),
+       "lac_ac_encode_uniform");
+    return LAC_OK;
+}
+
+int lac_ac_decode_uniform(int64_t n_streams, int64_t T, const int32_t* d_ntok, int32_t n_symbols,
+                          lac_dec_state* d_state, const uint8_t* d_bytes, const int64_t* d_offsets, int32_t* d_syms,
+                          int64_t sym_stride, int prec, void* stream) {
+    if (!d_state || !d_bytes || !d_offsets || (!d_syms && T > 0) || n_streams < 0 || T < 0 || n_symbols < 1)
+        return fail(LAC_E_ARG, "lac_ac_decode_uniform: bad argument");
+    if (!prec_ok(prec, 2)) return fail(LAC_E_ARG, "lac_ac_decode_uniform: prec %d outside [2, 60]", prec);
+    CK(lac::launch_uniform_decode(n_streams, T, d_ntok, n_symbols, d_state, d_bytes, d_offsets, d_syms, sym_stride,
+                                  prec, (cudaStream_t)stream),
+       "lac_ac_decode_uniform");
     return LAC_OK;
 }
 

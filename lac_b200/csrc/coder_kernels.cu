@@ -91,6 +91,87 @@ __global__ void encode_pairs_kernel(const uint2* __restrict__ pairs, int64_t n_s
     state[s].status = bw.status;
 }
 
+// ------------------------------------------------------------------ uniform Predictor(n) (arith_code.py:63-74)
+// The reference's base class maps symbol s of n to [floor(s w / n), floor((s + 1) w / n)) -- floor, not the ceil of
+// CDFPredictor.  AC() without arguments is AC(Predictor(3), 16).  One thread per stream.
+__global__ void uniform_encode_kernel(const int32_t* __restrict__ syms, int64_t n_streams, int64_t T, int64_t sym_stride,
+                                      const int32_t* __restrict__ ntok, int nsym, lac_enc_state* __restrict__ state,
+                                      uint8_t* __restrict__ out, int64_t out_stride, int finish, int P) {
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    int64_t l = state[s].low, h = state[s].high;
+    coder::BitWriter bw;
+    bw.open(out + s * out_stride, (uint64_t)out_stride, state[s].nbits);
+    bw.status = state[s].status;
+    const int64_t Ts = ntok ? (int64_t)ntok[s] : T;
+    for (int64_t t = 0; t < Ts; t++) {
+        const int sym = syms[s * sym_stride + t];
+        if (sym < 0 || sym >= nsym) {
+            bw.status |= LAC_ST_SYMBOL;
+            break;
+        }
+        const u128 w = (u128)(uint64_t)(h - l + 1);
+        const int64_t r0 = (int64_t)(((u128)(uint32_t)sym * w) / (uint32_t)nsym);          // symbol_to_range :68-69
+        const int64_t r1 = (int64_t)((((u128)(uint32_t)sym + 1) * w) / (uint32_t)nsym);
+        if (r1 <= r0) {  // zero-width symbol (w < n): the reference would never terminate
+            bw.status |= LAC_ST_TABLE;
+            break;
+        }
+        h = l + r1 - 1;  // receive_symbol :160-166
+        l += r0;
+        int k = coder::renorm_count((uint64_t)(h - l + 1), P);
+        int64_t E = coder::renorm_apply(l, h, P, k);
+        bw.append(E, k);
+    }
+    if (finish && !(bw.status & (LAC_ST_TABLE | LAC_ST_SYMBOL))) coder::ac_flush(l, h, P, bw);
+    bw.close();
+    state[s].low = l;
+    state[s].high = h;
+    state[s].nbits = bw.nbits;
+    state[s].status = bw.status;
+}
+
+// Decoder: the symbol whose floor-mapped range holds the code value, i.e. the largest s with
+// floor(s w / n) <= v - l, s = floor(((v - l + 1) n - 1) / w).  (The reference's val_to_symbol, (v n) // w, is not
+// that symbol at range boundaries; its decoder asserts there.  See tests/golden/ac_uniform.npz.)
+__global__ void uniform_decode_kernel(int64_t n_streams, int64_t T, const int32_t* __restrict__ ntok, int nsym,
+                                      lac_dec_state* __restrict__ state, const uint8_t* __restrict__ bytes,
+                                      const int64_t* __restrict__ offsets, int32_t* __restrict__ syms,
+                                      int64_t sym_stride, int P) {
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    int64_t l = state[s].low, h = state[s].high, v = state[s].value;
+    uint64_t pos = state[s].pos;
+    uint32_t status = state[s].status;
+    const uint8_t* data = bytes + offsets[s];
+    const uint64_t nbytes = (uint64_t)(offsets[s + 1] - offsets[s]);
+    const int64_t Ts = ntok ? (int64_t)ntok[s] : T;
+    for (int64_t t = 0; t < Ts; t++) {
+        const u128 w = (u128)(uint64_t)(h - l + 1);
+        const u128 x = (u128)(uint64_t)(v - l);
+        const int64_t sym = (int64_t)(((x + 1) * (uint32_t)nsym - 1) / w);
+        const int64_t r0 = (int64_t)(((u128)(uint64_t)sym * w) / (uint32_t)nsym);
+        const int64_t r1 = (int64_t)((((u128)(uint64_t)sym + 1) * w) / (uint32_t)nsym);
+        if (sym >= nsym || r1 <= r0) {
+            status |= LAC_ST_TABLE;
+            break;
+        }
+        h = l + r1 - 1;
+        l += r0;
+        const int64_t off = v - l;
+        int k = coder::renorm_count((uint64_t)(h - l + 1), P);
+        coder::renorm_apply(l, h, P, k);
+        v = l + (off << k) + (int64_t)coder::read_bits(data, nbytes, pos, k);
+        pos += (uint64_t)k;
+        syms[s * sym_stride + t] = (int32_t)sym;
+    }
+    state[s].low = l;
+    state[s].high = h;
+    state[s].value = v;
+    state[s].pos = pos;
+    state[s].status = status;
+}
+
 __global__ void enc_init_kernel(lac_enc_state* state, int64_t n, int P) {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -420,6 +501,24 @@ cudaError_t launch_encode_pairs(const uint32_t* pairs, int64_t n, int64_t T, int
     // long dependent chain, so more schedulers beat denser blocks
     encode_pairs_kernel<<<(unsigned)((n + 31) / 32), 32, 0, st>>>(reinterpret_cast<const uint2*>(pairs), n, T, ss,
                                                                   ts, ntok, state, out, out_stride, finish, P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_uniform_encode(const int32_t* syms, int64_t n, int64_t T, int64_t sym_stride, const int32_t* ntok,
+                                  int nsym, lac_enc_state* state, uint8_t* out, int64_t out_stride, int finish, int P,
+                                  cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    uniform_encode_kernel<<<(unsigned)((n + 31) / 32), 32, 0, st>>>(syms, n, T, sym_stride, ntok, nsym, state, out,
+                                                                    out_stride, finish, P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_uniform_decode(int64_t n, int64_t T, const int32_t* ntok, int nsym, lac_dec_state* state,
+                                  const uint8_t* bytes, const int64_t* offsets, int32_t* syms, int64_t sym_stride,
+                                  int P, cudaStream_t st) {
+    if (n == 0 || T == 0) return cudaSuccess;
+    uniform_decode_kernel<<<(unsigned)((n + 31) / 32), 32, 0, st>>>(n, T, ntok, nsym, state, bytes, offsets, syms,
+                                                                    sym_stride, P);
     return cudaGetLastError();
 }
 

@@ -145,7 +145,13 @@ int64_t orc_llama_minp(const int64_t *dist, int V) {
     return best;
 }
 /* symbol_to_range, arith_code.py:102-114 (same body as llama_compress.py:49-61). */
+/* tbl == NULL: the uniform base class Predictor(V), arith_code.py:63-74 (floor-mapped). */
 static int symbol_to_range(const int64_t *tbl, int V, int64_t s, i128 denom, i128 *r0, i128 *r1) {
+    if (!tbl) {                                   /* Predictor.symbol_to_range :68-69: no bound on s (the */
+        *r0 = fdiv((i128)s * denom, V);           /* decoder's flush() probes symbols past n - 1)          */
+        *r1 = fdiv((i128)(s + 1) * denom, V);
+        return ORC_OK;
+    }
     if (s >= V || s < 0) return ORC_E_SYMBOL;
     i128 hd = tbl[s];
     i128 ld = s > 0 ? tbl[s - 1] : 0;
@@ -156,6 +162,7 @@ static int symbol_to_range(const int64_t *tbl, int V, int64_t s, i128 denom, i12
 }
 /* val_to_symbol, arith_code.py:94-101: bisect_right(dist, (v*dist[-1])//denom). */
 static int64_t val_to_symbol(const int64_t *tbl, int V, i128 v, i128 denom) {
+    if (!tbl) return (int64_t)fdiv(v * (i128)V, denom);   /* Predictor.val_to_symbol :66-67 */
     i128 target = fdiv(v * (i128)tbl[V - 1], denom);
     int64_t lo = 0, hi = V;
     while (lo < hi) {
@@ -198,10 +205,15 @@ int orc_ac_encode(int prec, const int64_t *dist, int64_t stride, int64_t ntab, c
     for (int64_t t = 0; t < n && !sk.err; t++) {
         /* receive_symbol :160-166 */
         i128 w = h - l + 1, mp, r0, r1;
-        const int64_t *raw = table_at(dist, stride, ntab, V, t, minp, &mp);
-        const int64_t *tbl = fudged_dist(raw, V, mp, w, scratch, wrap64);
+        const int64_t *tbl = NULL;
+        if (dist) {
+            const int64_t *raw = table_at(dist, stride, ntab, V, t, minp, &mp);
+            tbl = fudged_dist(raw, V, mp, w, scratch, wrap64);
+        }
+        if (syms[t] < 0 || syms[t] >= V) { rc = ORC_E_SYMBOL; break; }
         rc = symbol_to_range(tbl, V, syms[t], w, &r0, &r1);
         if (rc) break;
+        if (r1 <= r0) { rc = ORC_E_ZERODIV; break; }   /* zero-width symbol: the reference loops forever */
         h = l + r1 - 1;
         l += r0;
         /* step :179-184 / decide_bit :167-171 / emit_bit :172-178 */
@@ -246,6 +258,7 @@ typedef struct {
 
 static const int64_t *afb_table(afb *d, i128 w) {
     i128 mp;
+    if (!d->dist) return NULL;   /* uniform Predictor(V) */
     const int64_t *raw = table_at(d->dist, d->stride, d->ntab, d->V, d->nout, d->minp, &mp);
     return fudged_dist(raw, d->V, mp, w, d->scratch, d->wrap64);
 }
@@ -292,7 +305,7 @@ static int afb_flush(afb *d) {
         int64_t ls = val_to_symbol(tbl, d->V, d->lb - d->l, w);
         int64_t hs = val_to_symbol(tbl, d->V, d->hb - d->l, w);
         if (ls > hs) return ORC_E_EMPTY;
-        int64_t best = -1; double bestk = 0;
+        int64_t best = 0; double bestk = 0; int have = 0;   /* the uniform Predictor can probe negative symbols */
         for (int64_t s = ls; s <= hs; s++) {
             i128 r0, r1;
             int rc = symbol_to_range(tbl, d->V, s, w, &r0, &r1);
@@ -300,7 +313,7 @@ static int afb_flush(afb *d) {
             if (r1 == r0) return ORC_E_ZERODIV;
             double k = (double)region_overlap(d->lb - d->l, d->hb - d->l, r0, r1 - 1) /
                        (double)(r1 - r0);
-            if (best < 0 || k > bestk) { best = s; bestk = k; }
+            if (!have || k > bestk) { best = s; bestk = k; have = 1; }
         }
         int rc = afb_emit_symbol(d, best);
         if (rc) return rc;
@@ -565,9 +578,16 @@ int orc_ac_decode_n(int prec, const int64_t *dist, int64_t stride, int64_t ntab,
     int rc = ORC_OK;
     for (int64_t t = 0; t < n; t++) {
         i128 w = h - l + 1, mp, r0, r1;
-        const int64_t *raw = table_at(dist, stride, ntab, V, t, minp, &mp);
-        const int64_t *tbl = fudged_dist(raw, V, mp, w, scratch, wrap64);
-        int64_t s = val_to_symbol(tbl, V, v - l, w);
+        const int64_t *tbl = NULL;
+        int64_t s;
+        if (dist) {
+            const int64_t *raw = table_at(dist, stride, ntab, V, t, minp, &mp);
+            tbl = fudged_dist(raw, V, mp, w, scratch, wrap64);
+            s = val_to_symbol(tbl, V, v - l, w);
+        } else {
+            /* the symbol whose floor-mapped range holds v - l: largest s with floor(s w / V) <= v - l */
+            s = (int64_t)fdiv((v - l + 1) * (i128)V - 1, w);
+        }
         rc = symbol_to_range(tbl, V, s, w, &r0, &r1);
         if (rc) break;
         h = l + r1 - 1;

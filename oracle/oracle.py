@@ -76,11 +76,30 @@ def lib():
 
 
 def _ptr(a):
+    if hasattr(a, "ctypes_ptr"):
+        return a.ctypes_ptr()
     return a.ctypes.data_as(C.c_void_p)
+
+
+class _Uniform:
+    """Stands for the reference's uniform base class Predictor(n) (arith_code.py:63-74)."""
+
+    def __init__(self, n):
+        self.n = int(n)
+
+    def ctypes_ptr(self):
+        return None
+
+
+def uniform(n):
+    """Pass as `dist` to ac_encode / ac_decode / ac_decode_n for AC(Predictor(n), prec)."""
+    return _Uniform(n)
 
 
 def _tables(dist, minp, kind="cdf"):
     """dist: [V] shared or [T, V] per-position int64 inclusive cumulative tables."""
+    if isinstance(dist, _Uniform):
+        return dist, 0, 1, dist.n, np.ones(1, dtype=np.int64)
     dist = np.ascontiguousarray(dist, dtype=np.int64)
     if dist.ndim == 1:
         stride, ntab, V = 0, 1, dist.shape[0]

@@ -315,6 +315,29 @@ def gen_acs_64k():
     np.savez_compressed(os.path.join(HERE, "acs_64k.npz"), seed=11, n=len(data), prec=prec,
                         data=np.frombuffer(data, dtype=np.uint8), comp=np.frombuffer(bytes(out), dtype=np.uint8))
     print("acs_64k:", len(data), "->", len(out), "bytes")
+# ---------------------------------------------------------------- arith_code: the uniform base class Predictor(n)
+def gen_ac_uniform(rng):
+    """AC(Predictor(n), prec) -- the reference's default coder is AC() = AC(ternary = Predictor(3), 16)."""
+    store, names = {}, []
+    for n in (2, 3, 5, 10, 256, 1000):
+        for prec in (16, 24, 32, 48):
+            if n >= (1 << (prec - 2)):
+                continue
+            coder = ac.AC(ac.Predictor(n), prec)
+            for length in (0, 1, 7, 60, 300):
+                syms = [int(s) for s in rng.integers(0, n, size=length)]
+                for stop in (0, 1):
+                    bits = [int(b) for b in coder.to_bin.bits(syms, stop)]
+                    r, blen = coder.to_bin.encode(syms, stop)
+                    assert blen == len(bits) and r == int("0" + "".join(map(str, bits)), 2)
+                    dec, err = run_decoder(coder, bits, stop)
+                    name = f"u{len(names)}"
+                    names.append(name)
+                    pack_case(store, name, prec=prec, n=n, syms=np.array(syms, dtype=np.int32), stop=stop,
+                              bits=np.array(bits, dtype=np.uint8), dec=np.array(dec, dtype=np.int32), dec_err=err)
+    store["names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "ac_uniform.npz"), **store)
+    print("ac_uniform:", len(names), "cases")
 
 
 if __name__ == "__main__":
@@ -324,3 +347,4 @@ if __name__ == "__main__":
     gen_ac_adaptive()
     gen_acs(rng)
     gen_acs_64k()
+    gen_ac_uniform(np.random.default_rng(20261019))

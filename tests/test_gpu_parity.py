@@ -491,3 +491,45 @@ def test_alternative_staging_paths_are_bit_exact(env):
     e.update(env)
     r = subprocess.run([sys.executable, "-c", _PATH_SCRIPT, root], env=e, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_golden_ac_uniform_predictor(golden_dir):
+    """AC(Predictor(n), prec), the reference's uniform floor-mapped base class (its default AC() is Predictor(3)
+    at 16 bits): GPU bytes identical to the reference's bits, decode returns the coded symbols; all 240 cases
+    batched per (n, prec, T, stop) would hide nothing, so they run one stream each plus one batched check."""
+    g = _golden(golden_dir, "ac_uniform.npz")
+    n_checked = n_dec = 0
+    for nm in g["names"]:
+        prec, stop, n = int(g[f"{nm}/prec"]), int(g[f"{nm}/stop"]), int(g[f"{nm}/n"])
+        syms = g[f"{nm}/syms"].astype(np.int32)
+        T = len(syms)
+        want = g[f"{nm}/bits"]
+        enc = coder.StreamEncoder(1, prec=prec, capacity_bytes=T * 8 + 64)
+        if T:
+            enc.encode_uniform(_dev(syms[None]), n, finish=bool(stop))
+        elif stop:
+            enc.finish()
+        streams, nbits = enc.bitstreams()
+        assert nbits[0] == len(want), nm
+        assert streams[0] == orc.pack_bits(want).tobytes(), nm
+        n_checked += 1
+        if stop and T:
+            out = coder.StreamDecoder([streams[0]], prec=prec).decode_uniform(n, T).cpu().numpy()[0]
+            assert np.array_equal(out, syms), nm
+            n_dec += 1
+    assert n_checked == 240 and n_dec >= 90
+    # many streams at once, ragged, and a symbol outside the alphabet flags its stream only
+    rng = np.random.default_rng(3)
+    S, T, n = 70, 50, 3
+    syms = rng.integers(0, n, (S, T)).astype(np.int32)
+    ntok = rng.integers(0, T + 1, S).astype(np.int32)
+    enc = coder.StreamEncoder(S, prec=16, capacity_bytes=T * 8 + 64)
+    enc.encode_uniform(_dev(syms), n, ntok=_dev(ntok), finish=True)
+    streams, nbits = enc.bitstreams()
+    for s in range(S):
+        want = orc.ac_encode(orc.uniform(n), syms[s, :ntok[s]], prec=16, stop=1)
+        assert nbits[s] == len(want) and streams[s] == orc.pack_bits(want).tobytes()
+    out = coder.StreamDecoder(streams, prec=16).decode_uniform(n, T, ntok=_dev(ntok)).cpu().numpy()
+    for s in range(S):
+        assert np.array_equal(out[s, :ntok[s]], syms[s, :ntok[s]])

@@ -83,6 +83,25 @@ def test_mirror_ac_on_goldens(golden_dir):
 
 @gpu
 @needs_gpu
+def test_mirror_default_coder_is_the_uniform_ternary_predictor(golden_dir):
+    """The reference's AC() is AC(Predictor(3), 16): same defaults, same bits, same round trip here."""
+    assert ac.AC().predictor.n == 3 and ac.AC().precision == 16
+    g = np.load(os.path.join(golden_dir, "ac_uniform.npz"))
+    n_default = 0
+    for nm in list(g["names"])[::4]:
+        prec, stop, n = int(g[f"{nm}/prec"]), int(g[f"{nm}/stop"]), int(g[f"{nm}/n"])
+        syms = [int(x) for x in g[f"{nm}/syms"]]
+        want = [int(b) for b in g[f"{nm}/bits"]]
+        coder_ = ac.AC() if (n, prec) == (3, 16) else ac.AC(ac.Predictor(n), prec)
+        n_default += (n, prec) == (3, 16)
+        assert list(coder_.to_bin.bits(syms, stop)) == want, nm
+        if stop and syms:
+            assert list(coder_.from_bin.run(want, stop, count=len(syms))) == syms, nm
+    assert n_default >= 2
+
+
+@gpu
+@needs_gpu
 def test_mirror_adaptive_model_matches_reference_bytes(golden_dir):
     g = np.load(os.path.join(golden_dir, "ac_adaptive.npz"))
     data = g["data"].tolist()

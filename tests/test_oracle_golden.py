@@ -114,3 +114,23 @@ def test_pack_unpack_roundtrip():
         assert len(by) == (n + 7) // 8
         assert np.array_equal(orc.unpack_bits(by)[:n], bits)
         assert not orc.unpack_bits(by)[n:].any()
+
+
+def test_ac_uniform_predictor(golden_dir):
+    """AC(Predictor(n), prec): the reference's uniform, floor-mapped base class (arith_code.py:63-74); its
+    default coder AC() is AC(Predictor(3), 16).  Encoder bit-exact, literal decoder identical including the
+    junk symbols its flush() appends (negative ones too), value-based decode returns the coded symbols."""
+    g = _load(golden_dir, "ac_uniform.npz")
+    names = list(g["names"])
+    assert len(names) >= 200
+    for nm in names:
+        prec, stop, n = int(g[f"{nm}/prec"]), int(g[f"{nm}/stop"]), int(g[f"{nm}/n"])
+        syms = g[f"{nm}/syms"]
+        bits = orc.ac_encode(orc.uniform(n), syms, prec=prec, stop=stop)
+        assert np.array_equal(bits, g[f"{nm}/bits"]), nm
+        dec, rc = orc.ac_decode(orc.uniform(n), g[f"{nm}/bits"], prec=prec, stop=stop)
+        err = str(g[f"{nm}/dec_err"])
+        assert np.array_equal(dec, g[f"{nm}/dec"]), (nm, err, rc)
+        assert (rc != 0) == (err != ""), (nm, err, rc)
+        if stop:
+            assert np.array_equal(orc.ac_decode_n(orc.uniform(n), bits, len(syms), prec=prec), syms), nm
