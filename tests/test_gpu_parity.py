@@ -533,3 +533,25 @@ def test_golden_ac_uniform_predictor(golden_dir):
     out = coder.StreamDecoder(streams, prec=16).decode_uniform(n, T, ntok=_dev(ntok)).cpu().numpy()
     for s in range(S):
         assert np.array_equal(out[s, :ntok[s]], syms[s, :ntok[s]])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("V", [1000, 32000, 65536])
+def test_special_rows_through_both_second_passes(V):
+    """Degenerate and hostile rows (all -inf, all NaN, a +inf, huge magnitudes, -inf holes) through
+    summary + pair + coder and summary + serial decode: pairs equal the oracle's, streams round-trip."""
+    rng = np.random.default_rng(V + 7)
+    rows = _special_rows(V, rng)                      # 15 rows
+    S, T = 3, len(rows)
+    logits = np.stack([rows[rng.permutation(T)] for _ in range(S)])
+    syms = rng.integers(0, V, (S, T)).astype(np.int32)
+    syms[0, :4] = [0, V - 1, V // 2, 1]
+    lo, hi = orc.lq32_lookup(logits.reshape(S * T, V), syms.reshape(-1))
+    pairs = coder.cdf_lookup(_dev(logits.reshape(S * T, V)), _dev(syms.reshape(-1))).cpu().numpy().view(np.uint32)
+    assert np.array_equal(pairs[:, 0], lo) and np.array_equal(pairs[:, 1].astype(np.uint64), hi & 0xFFFFFFFF)
+    enc = coder.StreamEncoder(S, capacity_bytes=T * 8 + 64)
+    enc.encode_logits(_dev(logits), _dev(syms), finish=True)
+    streams, _ = enc.bitstreams()
+    for s in range(S):
+        assert streams[s] == _oracle_stream(logits[s], syms[s], 48)
+    assert np.array_equal(coder.StreamDecoder(streams).decode_logits(_dev(logits)).cpu().numpy(), syms)
