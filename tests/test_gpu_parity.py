@@ -555,3 +555,48 @@ def test_special_rows_through_both_second_passes(V):
     for s in range(S):
         assert streams[s] == _oracle_stream(logits[s], syms[s], 48)
     assert np.array_equal(coder.StreamDecoder(streams).decode_logits(_dev(logits)).cpu().numpy(), syms)
+
+
+@pytest.mark.gpu
+def test_lookup_and_decode_are_cuda_graph_capturable():
+    """The device entry points are asynchronous and use only stream-ordered work (cudaMallocAsync scratch
+    included), so a model-in-the-loop step can be captured into a CUDA graph and replayed."""
+    rng = np.random.default_rng(9)
+    S, V = 64, 32000
+    logits = _dev((rng.standard_normal((S, 1, V)) * 4).astype(np.float32))
+    syms = _dev(rng.integers(0, V, (S, 1)).astype(np.int32))
+    ref_enc = coder.StreamEncoder(S, capacity_bytes=256)
+    ref_enc.encode_logits(logits, syms, finish=True)           # also warms the scratch pool up
+    want, _ = ref_enc.bitstreams()
+    enc = coder.StreamEncoder(S, capacity_bytes=256)
+    pairs = torch.empty((S, 2), dtype=torch.int32, device="cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    L = _ffi.lib()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            st = torch.cuda.current_stream().cuda_stream
+            _ffi.check(L.lac_cdf_lookup_f32(logits.data_ptr(), S, V, V, syms.data_ptr(), pairs.data_ptr(), None, st))
+            _ffi.check(L.lac_ac_encode_pairs(pairs.data_ptr(), S, 1, 1, 1, None, enc.state.data_ptr(),
+                                             enc.out.data_ptr(), enc.cap, 1, enc.prec, st))
+    torch.cuda.current_stream().wait_stream(side)
+    graph.replay()
+    torch.cuda.synchronize()
+    got, _ = enc.bitstreams()
+    assert got == want
+    # decode step captured the same way
+    dec = coder.StreamDecoder(want)
+    out = torch.zeros((S, 1), dtype=torch.int32, device="cuda")
+    g2 = torch.cuda.CUDAGraph()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g2, stream=side):
+            st = torch.cuda.current_stream().cuda_stream
+            _ffi.check(L.lac_ac_decode_logits_f32(logits.data_ptr(), S, 1, V, V, V, None, dec.state.data_ptr(),
+                                                  dec.bytes.data_ptr(), dec.offsets.data_ptr(), out.data_ptr(), 1,
+                                                  dec.prec, st))
+    torch.cuda.current_stream().wait_stream(side)
+    g2.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, syms)
