@@ -35,9 +35,9 @@ namespace lac {
 constexpr int kThreads = 1024;
 constexpr int kWarps = kThreads / 32;
 constexpr int kPerThread = 32;  // row elements held per thread
-// Row summary written by decode pass 1, uint64 words: [0] row reference nref, [1 .. CL] the CTAs' totals of q,
-// [1 + CL + 32 c + w] exclusive prefix of q inside CTA c at the start of its warp w.
-__host__ __device__ constexpr int summ_words(int cl) { return 1 + cl + cl * 32; }
+// Row summary written by pass 1, uint64 words: [0] row reference nref, [1 + 32 c + w] the total of q of warp w of
+// CTA part c.  Every warp writes its own word; nothing is reduced across warps in pass 1.
+__host__ __device__ constexpr int summ_words(int cl) { return 1 + cl * 32; }
 
 // TMA chunks per row.  Measured on B200 (profiles/microbench/tma_stream.cu): every cp.async.bulk costs
 // ~0.2 us of per-SM TMA time regardless of size, so 8 x 16 KB chunks cap at 4.7 TB/s while 2 x 64 KB
@@ -304,6 +304,16 @@ struct FlatSeq {
 __shared__ Ctl g_ctl;
 extern __shared__ __align__(128) unsigned char g_ring[];
 
+struct NoSummary {  // build_kernel: the finishing warp derives prefixes and scale inside the kernel
+    static constexpr bool kSummary = false;
+    __device__ __forceinline__ uint64_t* operator()() const { return nullptr; }
+};
+struct SummaryAt {  // summary_kernel: where this row's summary goes
+    static constexpr bool kSummary = true;
+    uint64_t* p;
+    __device__ __forceinline__ uint64_t* operator()() const { return p; }
+};
+
 template <int VEC, bool TMA, int NCH, int CL>
 struct RowEngine {
     static_assert(CL == 1 || (TMA && VEC == 4), "cluster rows use the TMA path");
@@ -460,6 +470,17 @@ struct RowEngine {
             lane_sum += (q[i] + q[i + 1]) + (q[i + 2] + q[i + 3]);
         }
         const uint64_t ws = warp_sum48(lane_sum);
+        if (SummFn::kSummary) {
+            // pass 1 of lookup / decode: every warp stores its own total; no counter, no finishing warp, no scan,
+            // nothing for the other warps to wait for at the next row's barrier
+            if (lane() == 0) {
+                uint64_t* out = summ();
+                out[1 + gwarp()] = ws;
+                if (gwarp() == 0) out[0] = (uint64_t)nrow_u;
+            }
+            it++;
+            return;
+        }
         uint32_t prev = 0;
         if (lane() == 0) {
             g_ctl.wsum[warp()] = ws;
@@ -468,32 +489,17 @@ struct RowEngine {
             asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(prev) : "r"(smem_u32(&g_ctl.arrive)) : "memory");
         }
         prev = __shfl_sync(0xffffffffu, prev, 0);
-        if (prev == kWarps - 1) finish_row(V, par, (it >> 1) & 1, summ(), nrow_u);  // last warp of the row: every wsum[] is visible
+        if (prev == kWarps - 1) finish_row(V, par, (it >> 1) & 1);  // last warp of the row: every wsum[] is visible
         it++;
     }
 
     // Row-level bookkeeping, run by exactly one warp per CTA per row.
-    // summ (decode, pass 1): row summary = { nref, total[CL], prefix[CL][32] } (see summ_words()).
-    static __device__ __noinline__ void finish_row(int V, uint32_t par, uint32_t ph, uint64_t* summ,
-                                                   uint32_t nrow_u) {
+    static __device__ __noinline__ void finish_row(int V, uint32_t par, uint32_t ph) {
         const int ln = lane();
         fence_acq_rel_cta();
         const uint64_t v = *reinterpret_cast<volatile uint64_t*>(&g_ctl.wsum[ln]);
         const uint64_t inc = warp_incl_scan(v, ln);
         uint64_t Q = __shfl_sync(0xffffffffu, inc, 31);
-        if (summ) {
-            // decode pass 1: this CTA's part of the row summary -- its total and the CTA-local exclusive prefix at
-            // each of its warps.  No exchange with the peers and no division: pass 2 adds the lower CTAs' totals
-            // and derives the scale itself.
-            summ[1 + CL + (int)Clu<CL>::rank() * kWarps + ln] = inc - v;
-            if (ln == 0) {
-                summ[1 + Clu<CL>::rank()] = Q;
-                if (Clu<CL>::rank() == 0) summ[0] = (uint64_t)nrow_u;
-                g_ctl.arrive = 0;
-                mbar_arrive(&g_ctl.done);
-            }
-            return;
-        }
         uint64_t base = 0;
         if (CL > 1) {  // exchange the CTA totals; base = total of the lower-ranked CTAs
             if (ln < CL) {
@@ -564,12 +570,15 @@ pair_kernel(const float* __restrict__ logits, int64_t rows, int64_t row_stride, 
     while (seg(gw + 1) <= gs) gw++;
     while (seg(gw) > gs) gw--;
     const int nref = (int)(uint32_t)tab[0];
-    uint64_t Q = 0, C = tab[1 + CL + gw];
+    // row total and the total of the warp segments in front of gw, from the 32 * CL warp sums (masked REDUX sums)
+    uint64_t qall = 0, qfront = 0;
     for (int c = 0; c < CL; c++) {
-        const uint64_t tot = tab[1 + c];
-        Q += tot;
-        if (c < (gw >> 5)) C += tot;
+        const uint64_t wsum = tab[1 + 32 * c + lane];
+        qall += wsum;
+        qfront += (32 * c + lane < gw) ? wsum : 0ull;
     }
+    const uint64_t Q = warp_sum48(qall);
+    const uint64_t C = warp_sum48(qfront);
     const lq::Scale sc = lq::make_scale(Q, V);
     const float* row = logits + r * row_stride;
     uint64_t part = 0;
@@ -630,8 +639,7 @@ build_kernel(const __grid_constant__ RowParams rp, int V, uint32_t* __restrict__
         const float* row = seq.ptr(rp);
         seq.next(rp, stride);
         uint32_t q[kPerThread];
-        eng.reduce(row, [&] { return seq.valid(rp) ? seq.ptr(rp) : nullptr; }, V, q,
-                   [] { return static_cast<uint64_t*>(nullptr); });
+        eng.reduce(row, [&] { return seq.valid(rp) ? seq.ptr(rp) : nullptr; }, V, q, NoSummary());
         const int warp = Eng::warp(), lane = Eng::lane(), gbeg = Eng::gbeg(V), gend = Eng::gend(V);
         eng.wait_done();
         uint64_t base = ctl.pref[warp];
@@ -709,7 +717,7 @@ summary_kernel(const __grid_constant__ RowParams rp, int V, uint64_t* __restrict
         seq.next(rp);
         uint32_t q[kPerThread];
         eng.reduce(row, [&] { return seq.valid(rp) ? seq.ptr(rp) : nullptr; }, V, q,
-                   [&] { return summ + idx * summ_words(CL); });
+                   SummaryAt{summ + idx * summ_words(CL)});
     }
     Eng::teardown();
 }
@@ -727,20 +735,28 @@ summary_kernel(const __grid_constant__ RowParams rp, int V, uint64_t* __restrict
 // not depend on the coder state) is computed while token t's segment is in flight.
 template <int CL>
 struct RowTab {
-    uint64_t nref, tot[CL], pre[CL];  // pre: CTA-local prefix at warp `lane` of CTA part c
+    uint64_t nref, Q, pre[CL];  // pre[j]: row-wide exclusive prefix of q at the start of row-wide warp lane * CL + j
+    // load: the CL consecutive warp sums of this lane (into pre[]); scan(): one warp scan of the lane totals turns
+    // them into prefixes and the row total.  Both are independent of the coder state, so they run one token ahead,
+    // under the previous token's segment loads.
     __device__ __forceinline__ void load(const uint64_t* tab, int lane) {
         nref = tab[0];
 #pragma unroll
-        for (int c = 0; c < CL; c++) {
-            tot[c] = tab[1 + c];
-            pre[c] = tab[1 + CL + 32 * c + lane];
-        }
+        for (int j = 0; j < CL; j++) pre[j] = tab[1 + lane * CL + j];
     }
-    __device__ __forceinline__ uint64_t total() const {
-        uint64_t Q = 0;
+    __device__ __forceinline__ void scan(int lane) {
+        uint64_t tot = 0;
 #pragma unroll
-        for (int c = 0; c < CL; c++) Q += tot[c];
-        return Q;
+        for (int j = 0; j < CL; j++) tot += pre[j];
+        const uint64_t inc = warp_incl_scan(tot, lane);
+        uint64_t run = inc - tot;
+#pragma unroll
+        for (int j = 0; j < CL; j++) {
+            const uint64_t w = pre[j];
+            pre[j] = run;
+            run += w;
+        }
+        Q = __shfl_sync(0xffffffffu, inc, 31);
     }
 };
 
@@ -768,35 +784,36 @@ decode_serial_kernel(const __grid_constant__ RowParams rp, int V, const uint64_t
     const uint64_t* tab = summ + (s * rp.T) * words;
     RowTab<CL> cur, nxt;
     cur.load(tab, lane);
-    lq::Scale sc = lq::make_scale(cur.total(), V);
+    cur.scan(lane);
+    lq::Scale sc = lq::make_scale(cur.Q, V);
     nxt = cur;
     if (Ts > 1) nxt.load(tab + words, lane);
     for (int t = 0; t < Ts; t++, tab += words, row += rp.st) {
         const int nref = (int)(uint32_t)cur.nref;
         const uint64_t w = (uint64_t)(high - low + 1), xr = (uint64_t)(value - low);
         const uint32_t target = lq::div_q32(xr >> 32, xr << 32, w);
-        // ---- level 1: lane l looks at warp l of every CTA part (row-wide warp 32 c + l)
+        // ---- level 1: lane l looks at the row-wide warps l * CL .. l * CL + CL - 1
         int best = -1;
-        uint64_t Cb = 0, base = 0;
+        uint64_t Cb = 0;
 #pragma unroll
         for (int c = 0; c < CL; c++) {
-            const int gw = 32 * c + lane;
-            const uint64_t C = base + cur.pre[c];
+            const int gw = lane * CL + c;
+            const uint64_t C = cur.pre[c];
             const int gb = seg(gw), ge = seg(gw + 1);
             const bool okw = (gb < ge) & (lq::cum_of(C, (uint32_t)(gb * VEC), sc) <= target);
             best = okw ? gw : best;
             Cb = okw ? C : Cb;
-            base += cur.tot[c];
         }
         const int gsel = __reduce_max_sync(0xffffffffu, best);  // >= 0: the first non-empty segment starts at cum 0
-        Cb = __shfl_sync(0xffffffffu, Cb, gsel & 31);
+        Cb = __shfl_sync(0xffffffffu, Cb, gsel / CL);
         const int e0 = seg(gsel) * VEC + 32 * lane, eend = seg(gsel + 1) * VEC;
         // ---- level 2: q of this lane's 32 consecutive elements.  All loads first (unconditional, from addresses
         // clamped into the segment), then branch-free arithmetic: the HBM latency is paid once per token.
         const lq::Scale sc_now = sc;
         auto advance = [&]() {  // while the segment is in flight: next token's scale, then the summary after that
             cur = nxt;
-            sc = lq::make_scale(cur.total(), V);
+            cur.scan(lane);  // (harmless on the last token: it rescans values nobody reads)
+            sc = lq::make_scale(cur.Q, V);
             if (t + 2 < Ts) nxt.load(tab + 2 * words, lane);
         };
         uint32_t r[kPerThread];
