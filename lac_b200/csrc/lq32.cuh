@@ -60,18 +60,30 @@ struct Scale {
     int s;
 };
 
-// floor(((hi << 64) | lo) / den) for a quotient known to fit 32 bits (den < 2^62): fp64 estimate, off by at
-// most one, then an exact fix-up.  Branch-free, so different lanes can divide different operands together.
+// floor(((hi << 64) | lo) / den) for a quotient known to fit 32 bits (den < 2^62, den >= 1): fp64 estimate, then
+// an exact fix-up.  The estimate is num * (1 / den) with the reciprocal from MUFU.RCP64H (rcp.approx.ftz.f64,
+// ~20 bits) refined by two Newton steps (relative error ~2^-52), so the truncated product is within one of the
+// true quotient; the remainder test below corrects up to two in either direction.  (A __ddiv_rz here costs a
+// ~150-clock subroutine call on the serial decode path.)  Branch-free, so lanes can divide different operands.
 __device__ __forceinline__ uint32_t div_q32(uint64_t hi, uint64_t lo, uint64_t den) {
+    const double d = (double)den;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = __fma_rn(__fma_rn(-d, r, 1.0), r, r);
+    r = __fma_rn(__fma_rn(-d, r, 1.0), r, r);
     const double num = __fma_rn((double)hi, 18446744073709551616.0, (double)lo);
-    uint64_t q = (uint64_t)__ddiv_rz(num, (double)den);
-    // remainder r = num - q * den as a signed 128-bit value, via 64-bit halves
-    const uint64_t plo = q * den, phi = __umul64hi(q, den);
-    const uint64_t rlo = lo - plo;
-    const int64_t rhi = (int64_t)(hi - phi - (lo < plo ? 1u : 0u));
-    const bool neg = rhi < 0;
-    const bool big = !neg && (rhi > 0 || rlo >= den);
-    return (uint32_t)(q - (neg ? 1u : 0u) + (big ? 1u : 0u));
+    uint64_t q = (uint64_t)__dmul_rz(num, r);
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+        // remainder rem = num - q * den as a signed 128-bit value, via 64-bit halves
+        const uint64_t plo = q * den, phi = __umul64hi(q, den);
+        const uint64_t rlo = lo - plo;
+        const int64_t rhi = (int64_t)(hi - phi - (lo < plo ? 1u : 0u));
+        const bool neg = rhi < 0;
+        const bool big = !neg && (rhi > 0 || rlo >= den);
+        q = q - (neg ? 1u : 0u) + (big ? 1u : 0u);
+    }
+    return (uint32_t)q;
 }
 
 __device__ __forceinline__ Scale make_scale(uint64_t Q, int V) {
