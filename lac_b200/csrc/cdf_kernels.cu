@@ -14,10 +14,10 @@
 //            mbarriers and issue the bulk copies of the CTA's NEXT row, so 128 KB per SM are in flight
 //            during the compute phase.  In a cluster the CTA maxima then cross DSMEM (st.async).
 //   phase B  q_i with packed fp32x2 math (FADD2 / FFMA2), exact integer sums (lane -> warp)
-//   finish   the LAST warp to finish phase B (shared-memory atomic counter) scans the 32 warp totals and writes
-//            the row summary {nref, total[CL], prefix[CL][32]} (272 bytes per 32000-element row); no division,
-//            no table, nobody waits for it.  (build_kernel, the full-table variant, also derives the scale and
-//            publishes it through the `done` mbarrier.)
+//   finish   lane 0 of EVERY warp stores the warp's total into the row summary {nref, wsum[32 * CL]} (264 bytes
+//            per 32000-element row): no counter, no finishing warp, no scan, no division, no table.
+//            (build_kernel, the full-table variant, keeps a last-arriving warp that derives prefixes and scale
+//            and publishes them through the `done` mbarrier.)
 //
 // The second passes work from the summary and re-read only the one warp segment (<= 4 KB) they need; q is a
 // function of (x, nref) only (lq32.cuh), so the recomputed values are bit-identical to pass 1 and the result does
@@ -371,9 +371,9 @@ struct RowEngine {
     // One row: stage it into registers, phase A (maximum), the row's single block barrier (plus, in a cluster,
     // the exchange of the CTA maxima), phase B (q, sums).  `next_row` (or nullptr) is prefetched as soon as this
     // row has left shared memory.  On return q[] holds this thread's q values; the row-level results
-    // (g_ctl.pref, Q, R, s) are valid once wait_done() returns.  summ != nullptr: the finishing warp also writes
-    // the row summary (reference, scale, warp-segment prefixes) there.
-    // next_row() and summ() are evaluated lazily, by the chunk leaders resp. the finishing warp only: pointer
+    // (g_ctl.pref, Q, R, s) are valid once wait_done() returns -- unless SummFn::kSummary, in which case every warp
+    // just stores its total into the row summary and there is no row-level bookkeeping at all.
+    // next_row() and summ() are evaluated lazily, by the chunk leaders resp. lane 0 of each warp only: pointer
     // arithmetic every thread would otherwise redo per row costs issue slots the row loop does not have.
     template <class NextFn, class SummFn>
     __device__ __forceinline__ void reduce(const float* __restrict__ row, NextFn next_row, int V,
@@ -699,9 +699,9 @@ __device__ __forceinline__ uint64_t load_be64(const uint8_t* data, uint64_t nbyt
 }
 
 // ---- pass 1: row summaries.  The same engine as LOOKUP without an owner: rows are dealt to the CTAs / clusters
-// regardless of their stream (a 4-stream job still fills the machine), and the only output is the summary the
-// finishing warp of each CTA writes -- 8 + 264 * CL bytes per row next to the 4 * V bytes read.  No division and,
-// in a cluster, no exchange of totals: the only cluster traffic left is the row maximum.
+// regardless of their stream (a 4-stream job still fills the machine), and the only output is the summary --
+// 8 + 256 * CL bytes per row next to the 4 * V bytes read, one word per warp.  No division and, in a cluster, no
+// exchange of totals: the only cluster traffic left is the row maximum.
 template <int VEC, bool TMA, int NCH, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 summary_kernel(const __grid_constant__ RowParams rp, int V, uint64_t* __restrict__ summ) {
