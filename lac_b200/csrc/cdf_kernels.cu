@@ -545,15 +545,21 @@ struct RowEngine {
 // Pass 1 is summary_kernel (below); this pass is one warp per row, all rows independent: find the warp segment
 // of the symbol, re-read the part of it in front of the symbol (<= 4 KB, half of that on average), q against the
 // row reference, masked integer sums, two multiply-shifts.  ~3 % extra HBM traffic, a few microseconds per 16k rows.
-template <int VEC>
+template <int VEC, int CL>
 __global__ void __launch_bounds__(256)
-pair_kernel(const float* __restrict__ logits, int64_t rows, int64_t row_stride, int V, int cl_log2,
+pair_kernel(const float* __restrict__ logits, int64_t rows, int64_t row_stride, int V,
             const uint64_t* __restrict__ summ, const int32_t* __restrict__ syms, uint32_t* __restrict__ pairs,
             uint32_t* __restrict__ status) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= rows) return;
+    // everything that does not depend on the symbol is requested together with it
+    const uint64_t* tab = summ + r * summ_words(CL);
     const int sym = __ldg(syms + r);
+    const int nref = (int)(uint32_t)__ldg(tab);
+    uint64_t wsum[CL];
+#pragma unroll
+    for (int c = 0; c < CL; c++) wsum[c] = __ldg(tab + 1 + 32 * c + lane);
     if (sym < 0 || sym >= V) {
         if (lane == 0) {
             *reinterpret_cast<uint2*>(pairs + 2 * r) = make_uint2(0u, 0u);
@@ -561,21 +567,20 @@ pair_kernel(const float* __restrict__ logits, int64_t rows, int64_t row_stride, 
         }
         return;
     }
-    const int CL = 1 << cl_log2, groups = V / VEC, tw = kWarps << cl_log2;
-    auto seg = [&](int gw) { return (int)(((int64_t)gw * groups) >> (5 + cl_log2)); };  // RowEngine::seg_begin
-    const uint64_t* tab = summ + r * summ_words(CL);
+    constexpr int tw = kWarps * CL;
+    const int groups = V / VEC;
+    auto seg = [&](int gw) { return (int)(((int64_t)gw * groups) / tw); };  // RowEngine::seg_begin
     const int gs = sym / VEC;
-    int gw = (int)(((int64_t)gs * tw) / groups);  // the row-wide warp whose segment holds group gs (+- 1)
+    int gw = (int)(((uint32_t)gs * (uint32_t)tw) / (uint32_t)groups);  // the warp whose segment holds group gs (+- 1)
     gw = gw >= tw ? tw - 1 : gw;
     while (seg(gw + 1) <= gs) gw++;
     while (seg(gw) > gs) gw--;
-    const int nref = (int)(uint32_t)tab[0];
     // row total and the total of the warp segments in front of gw, from the 32 * CL warp sums (masked REDUX sums)
     uint64_t qall = 0, qfront = 0;
+#pragma unroll
     for (int c = 0; c < CL; c++) {
-        const uint64_t wsum = tab[1 + 32 * c + lane];
-        qall += wsum;
-        qfront += (32 * c + lane < gw) ? wsum : 0ull;
+        qall += wsum[c];
+        qfront += (32 * c + lane < gw) ? wsum[c] : 0ull;
     }
     const uint64_t Q = warp_sum48(qall);
     const uint64_t C = warp_sum48(qfront);
@@ -1044,11 +1049,6 @@ static int64_t summ_chunk_rows(int cl) {  // LAC_SUMMARY_BYTES: test switch, for
     const int64_t rows = budget / (summ_words(cl) * 8);
     return rows < 1 ? 1 : rows;
 }
-static int log2_of(int cl) {
-    int l = 0;
-    while ((1 << l) < cl) l++;
-    return l;
-}
 
 // Encode side: summary pass + one warp per row for the pair.
 cudaError_t launch_lookup(const float* logits, int64_t rows, int V, int64_t row_stride, const int32_t* syms,
@@ -1069,10 +1069,14 @@ cudaError_t launch_lookup(const float* logits, int64_t rows, int V, int64_t row_
         if (e != cudaSuccess) break;
         const unsigned blocks = (unsigned)((rn + 7) / 8);
         uint32_t* stat = status ? status + r0 : nullptr;
-        if (path == 0)
-            pair_kernel<1><<<blocks, 256, 0, st>>>(base, rn, row_stride, V, log2_of(cl), summ, syms + r0, pairs + 2 * r0, stat);
-        else
-            pair_kernel<4><<<blocks, 256, 0, st>>>(base, rn, row_stride, V, log2_of(cl), summ, syms + r0, pairs + 2 * r0, stat);
+#define LAC_PAIR(VEC_, CL_) \
+    pair_kernel<VEC_, CL_><<<blocks, 256, 0, st>>>(base, rn, row_stride, V, summ, syms + r0, pairs + 2 * r0, stat)
+        if (path == 0) LAC_PAIR(1, 1);
+        else if (cl == 1) LAC_PAIR(4, 1);
+        else if (cl == 2) LAC_PAIR(4, 2);
+        else if (cl == 4) LAC_PAIR(4, 4);
+        else LAC_PAIR(4, 8);
+#undef LAC_PAIR
         e = cudaGetLastError();
     }
     const cudaError_t ef = cudaFreeAsync(summ, st);
