@@ -46,10 +46,12 @@ def workload_config(n_gpus):
         "vocab": VOCAB,
         "streams_per_gpu": STREAMS,
         "tokens_per_stream": CHUNK_TOKENS,
-        "step": f"[{STREAMS} streams x {SLICE} tokens] slice, encode + decode, each slice a self-contained chunk "
-                f"({CHUNK_TOKENS // SLICE} steps = one full job)",
+        "step": f"one full job: {STREAMS} streams x {CHUNK_TOKENS} tokens encoded, then decoded, as {CHUNK_TOKENS // SLICE} "
+                f"slices of [{STREAMS} x {SLICE}] with the coder state carried (init once, flush once)",
         "prec": PREC,
-        "l2": f"inputs larger than L2: {STREAMS * SLICE * VOCAB * 4 / 1e9:.2f} GB of logits per step vs 126 MB",
+        "l2": f"inputs larger than L2: {STREAMS * SLICE * VOCAB * 4 / 1e9:.2f} GB of logits per slice vs 126 MB "
+              f"(the {STREAMS * CHUNK_TOKENS * VOCAB * 4 / 1e9:.0f} GB of a whole job do not fit in HBM: every slice reads the "
+              "same resident buffer with its own symbols)",
         "parallelism": f"chunk-sharded x{n_gpus}, no data-path collective",
     }
 
@@ -57,7 +59,7 @@ def workload_config(n_gpus):
 def measured_traffic(kernel, vocab, rows):
     """DRAM bytes per launch from the committed ncu capture, if it is for this exact workload; else None."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1", "traffic.json")))[kernel]
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2", "traffic.json")))[kernel]
         return t["dram_bytes"] if (t["vocab"], t["rows"]) == (vocab, rows) else None
     except Exception:
         return None
@@ -175,6 +177,87 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------ GPU legs
+class Job:
+    """One full coder job on one GPU: S streams x CHUNK tokens coded as CHUNK / SLICE slices with the coder state
+    carried from slice to slice (lac_enc_init once, finish once, lac_dec_init once).  The logits of a full job
+    (S x CHUNK x V fp32 = 268 GB at configs[1]) do not fit in HBM, so every slice reads the same resident
+    [S, SLICE, V] buffer (2.1 GB >> L2) with its own symbols."""
+
+    def __init__(self, L, ffi, torch, dev, S, T, V, chunk_tokens, seed):
+        self.L, self.ffi, self.torch = L, ffi, torch
+        self.S, self.T, self.V, self.n_slices = S, T, V, chunk_tokens // T
+        self.rows = S * T
+        self.cap = chunk_tokens * 8 + 64
+        gen = torch.Generator(device=dev).manual_seed(seed)
+        self.logits = torch.randn((S, T, V), generator=gen, device=dev) * 3.0
+        # symbols drawn from the model distribution (what an LLM coder sees on in-distribution text):
+        # n_slices independent draws per logits row, slice k uses draw k
+        probs = torch.softmax(self.logits.view(self.rows, V), -1)
+        draws = torch.multinomial(probs, self.n_slices, replacement=True, generator=gen)  # [rows, n_slices]
+        del probs
+        self.syms = draws.t().contiguous().view(self.n_slices, S, T).to(torch.int32)       # slice-major
+        self.back = torch.zeros_like(self.syms)
+        self.enc_state = torch.zeros((S, ffi.ENC_STATE_BYTES), dtype=torch.uint8, device=dev)
+        self.dec_state = torch.zeros((S, ffi.DEC_STATE_BYTES), dtype=torch.uint8, device=dev)
+        self.out = torch.zeros((S, self.cap), dtype=torch.uint8, device=dev)
+        self.offsets = torch.arange(S + 1, device=dev, dtype=torch.int64) * self.cap
+        self.ws_bytes = int(L.lac_workspace_bytes(self.rows, V))     # caller-provided scratch: no allocation per call
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.stream = torch.cuda.current_stream().cuda_stream
+        # kernels per job: enc_init + n x (summary, encode_fused) + dec_init + n x (summary, decode_serial)
+        self.launches = 2 + 4 * self.n_slices
+
+    def encode(self, ev=None):
+        L, ck, S, T, V, st = self.L, self.ffi.check, self.S, self.T, self.V, self.stream
+        ck(L.lac_enc_init(self.enc_state.data_ptr(), S, PREC, st))
+        for k in range(self.n_slices):
+            if ev is not None: ev[k][0].record()
+            # summary pass (fused softmax -> quantise -> clamp -> segment sums, one HBM pass over the logits), then
+            # ONE kernel: (lo, hi) of the coded symbols + range coder, bytes staged in shared memory
+            ck(L.lac_ac_encode_logits_f32(self.logits.data_ptr(), S, T, T * V, V, V, self.syms[k].data_ptr(), T, None,
+                                          self.enc_state.data_ptr(), self.out.data_ptr(), self.cap,
+                                          int(k == self.n_slices - 1), PREC, self.ws.data_ptr(), self.ws_bytes, st))
+            if ev is not None: ev[k][1].record()
+
+    def decode(self, ev=None):
+        L, ck, S, T, V, st = self.L, self.ffi.check, self.S, self.T, self.V, self.stream
+        ck(L.lac_dec_init(self.dec_state.data_ptr(), S, PREC, self.out.data_ptr(), self.offsets.data_ptr(), st))
+        for k in range(self.n_slices):
+            if ev is not None: ev[k][2].record()
+            # row summaries from the same logits (bandwidth-bound pass), then the serial pass per stream
+            ck(L.lac_ac_decode_logits_f32(self.logits.data_ptr(), S, T, T * V, V, V, None,
+                                          self.dec_state.data_ptr(), self.out.data_ptr(), self.offsets.data_ptr(),
+                                          self.back[k].data_ptr(), T, PREC, self.ws.data_ptr(), self.ws_bytes, st))
+            if ev is not None: ev[k][3].record()
+
+    def nbits(self):
+        return self.enc_state.view(self.torch.int64).view(self.S, 4)[:, 2]
+
+    def check(self):
+        assert self.torch.equal(self.back, self.syms), "round trip failed"
+        st = self.enc_state.view(self.torch.int32).view(self.S, 8)[:, 6]
+        assert int(st.max().item()) == 0, "encoder status set"
+        st = self.dec_state.view(self.torch.int32).view(self.S, 10)[:, 8]
+        assert int(st.max().item()) == 0, "decoder status set"
+
+    def events(self):
+        E = self.torch.cuda.Event
+        return [[E(enable_timing=True) for _ in range(4)] for _ in range(self.n_slices)]
+
+    @staticmethod
+    def slice_times(evs_list):
+        """mean ms per slice of (encode call, decode call) over the recorded jobs"""
+        enc = statistics.mean(e[0].elapsed_time(e[1]) for evs in evs_list for e in evs)
+        dec = statistics.mean(e[2].elapsed_time(e[3]) for evs in evs_list for e in evs)
+        return enc, dec
+
+
+def roofline_numbers(rows, V, encode_ms, decode_ms):
+    """algorithmic bytes of one call (the logits once, one symbol per row) and the two achieved GB/s figures"""
+    alg = rows * (V * 4 + 4)
+    return alg, alg / (encode_ms * 1e-3) / 1e9, alg / (decode_ms * 1e-3) / 1e9
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -191,65 +274,40 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
 
     S, T, V = STREAMS, SLICE, VOCAB
-    rows = S * T
-    cap = T * 8 + 64
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    logits = torch.randn((S, T, V), generator=gen, device=dev) * 3.0
-    # symbols drawn from the model distribution (what an LLM coder sees on in-distribution text)
-    syms = torch.multinomial(torch.softmax(logits.view(rows, V), -1), 1, generator=gen).view(S, T).to(torch.int32)
-    pairs = torch.empty((rows, 2), dtype=torch.int32, device=dev)
-    enc_state = torch.zeros((S, _ffi.ENC_STATE_BYTES), dtype=torch.uint8, device=dev)
-    dec_state = torch.zeros((S, _ffi.DEC_STATE_BYTES), dtype=torch.uint8, device=dev)
-    out = torch.zeros((S, cap), dtype=torch.uint8, device=dev)
-    offsets = (torch.arange(S + 1, device=dev, dtype=torch.int64) * cap)
-    back = torch.zeros((S, T), dtype=torch.int32, device=dev)
+    job = Job(L, _ffi, torch, dev, S, T, V, CHUNK_TOKENS, 1234 + rank)
+    rows = job.rows
     gathered = torch.zeros((world, S), dtype=torch.int64, device=dev) if world > 1 else None
-    stream = torch.cuda.current_stream().cuda_stream
-    ck = _ffi.check
 
     def step(ev=None):
-        # encode side: fused softmax -> quantise -> clamp -> prefix sums (summary pass), (lo, hi) of the coded symbol
-        # (pair pass), then the range coder
-        ck(L.lac_enc_init(enc_state.data_ptr(), S, PREC, stream))
-        if ev: ev[0].record()
-        ck(L.lac_cdf_lookup_f32(logits.data_ptr(), rows, V, V, syms.data_ptr(), pairs.data_ptr(), None, stream))
-        if ev: ev[1].record()
-        ck(L.lac_ac_encode_pairs(pairs.data_ptr(), S, T, T, 1, None, enc_state.data_ptr(), out.data_ptr(), cap, 1,
-                                 PREC, stream))
-        if ev: ev[2].record()
-        # decode side: row summaries from the same logits (bandwidth-bound pass), then the serial pass per stream
-        # (probe -> segment -> re-read 4 KB -> symbol -> narrow / renormalise)
-        ck(L.lac_dec_init(dec_state.data_ptr(), S, PREC, out.data_ptr(), offsets.data_ptr(), stream))
-        ck(L.lac_ac_decode_logits_f32(logits.data_ptr(), S, T, T * V, V, V, None, dec_state.data_ptr(),
-                                      out.data_ptr(), offsets.data_ptr(), back.data_ptr(), T, PREC, stream))
-        if ev: ev[3].record()
-        if world > 1:  # the one collective: per-stream bit lengths for the container index
-            nb = enc_state.view(torch.int64).view(S, 4)[:, 2].contiguous()
-            dist.all_gather_into_tensor(gathered.view(-1), nb)
-    launches_per_step = 7  # enc_init, summary, pair, encode_pairs | dec_init, summary, decode_serial
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    assert torch.equal(back, syms), "round trip failed"
-    nbits = enc_state.view(torch.int64).view(S, 4)[:, 2]
-    bits_per_token = float(nbits.sum().item()) / rows
+        job.encode(ev)
+        if world > 1:  # the one collective of a job: per-stream bit lengths for the container index
+            dist.all_gather_into_tensor(gathered.view(-1), job.nbits().contiguous())
+        job.decode(ev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    job.check()
+    tokens_per_job = S * CHUNK_TOKENS
+    bits_per_token = float(job.nbits().sum().item()) / tokens_per_job
+
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
         time.sleep(0.3)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    n_ev = min(args.steps, 4)  # per-slice CUDA events on the first few jobs (the kernels' own times)
+    evs = [job.events() for _ in range(n_ev)]
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_beg.record()
     for k in range(args.steps):
-        step(evs[k])
+        step(evs[k] if k < n_ev else None)
     t_end.record()
     barrier()
     elapsed_ms = t_beg.elapsed_time(t_end)
@@ -257,22 +315,59 @@ def run_gpu(args):
         t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
-    assert torch.equal(back, syms), "round trip failed in the timed region"
-    lookup_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
-    coder_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
-    decode_ms = statistics.mean(e[2].elapsed_time(e[3]) for e in evs)
+    clk = clocks.stop() if rank == 0 else None
+    job.check()
+    encode_ms, decode_ms = Job.slice_times(evs)
+
+    # ---------------- the north-star target shape: vocab 128256 (configs[3] / [4]), same 2.1 GB per slice
+    v128 = None
+    if rank == 0 and not args.no_v128 and V != 128256:
+        V2, S2 = 128256, 256
+        job2 = Job(L, _ffi, torch, dev, S2, T, V2, args.v128_tokens, 99)
+        for _ in range(3):
+            job2.encode(); job2.decode()
+        torch.cuda.synchronize()
+        job2.check()
+        clocks2 = Clocks(local)
+        clocks2.start()
+        time.sleep(0.3)
+        evs2 = [job2.events() for _ in range(args.v128_jobs)]
+        b2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        b2.record()
+        for ev in evs2:
+            job2.encode(ev); job2.decode(ev)
+        e2.record()
+        torch.cuda.synchronize()
+        ms2 = b2.elapsed_time(e2)
+        clk2 = clocks2.stop()
+        job2.check()
+        l2, d2 = Job.slice_times(evs2)
+        peak, _ = peaks()
+        alg2, lg2, dg2 = roofline_numbers(job2.rows, V2, l2, d2)
+        v128 = {"workload": f"vocab {V2}, {S2} streams x {args.v128_tokens} tokens in slices of {T}, encode+decode, "
+                            f"{job2.rows * V2 * 4 / 1e9:.2f} GB of logits per slice",
+                "encode": {"ms": l2, "achieved": lg2, "frac": lg2 / peak, "algorithmic_bytes_per_call": alg2},
+                "decode": {"ms": d2, "achieved": dg2, "frac": dg2 / peak},
+                "tokens_per_s": S2 * args.v128_tokens * args.v128_jobs / (ms2 * 1e-3),
+                "jobs": args.v128_jobs, "ms_total": ms2, "clocks": clk2,
+                "bits_per_token": float(job2.nbits().sum().item()) / (S2 * args.v128_tokens)}
+        del job2
+        torch.cuda.empty_cache()
 
     # ---------------- e2e: HOST buffers through the C ABI, copies inside the timed region
     e2e = None
     if not args.no_e2e:
+        cap = T * 8 + 64
         e_steps = max(2, min(args.steps, args.e2e_steps))
         h_logits = torch.empty((S, T, V), dtype=torch.float32).pin_memory()
-        h_logits.copy_(logits)
-        h_syms = syms.cpu().pin_memory()
+        h_logits.copy_(job.logits)
+        h_syms = job.syms[0].cpu().pin_memory()
         h_out = torch.zeros((S, cap), dtype=torch.uint8).pin_memory()
         h_nbits = torch.zeros(S, dtype=torch.int64).pin_memory()
         h_back = torch.zeros((S, T), dtype=torch.int32).pin_memory()
         h_offs = (torch.arange(S + 1, dtype=torch.int64) * cap)
+        ck = _ffi.check
 
         def host_step():
             ck(L.lac_encode_logits_host(h_logits.data_ptr(), h_syms.data_ptr(), S, T, V, h_out.data_ptr(), cap,
@@ -295,33 +390,39 @@ def run_gpu(args):
         d2h = S * cap + S * _ffi.ENC_STATE_BYTES + rows * 4
         e2e = {"value": world * rows * e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": e_steps, "ms_per_step": dt / e_steps * 1e3,
+               "step": f"one [{S} x {T}] slice of the job, host logits in, host bytes / symbols out",
+               "bound": "pcie", "h2d_gbps": h2d * e_steps / dt / 1e9,
                "api": "lac_encode_logits_host + lac_decode_logits_host (pinned host logits in, host bytes/symbols out)"}
-    clk = clocks.stop() if rank == 0 else None
 
     if rank == 0:
         peak, peak_src = peaks()
-        alg_bytes = rows * (V * 4 + 4 + 8)
-        look_gbs = alg_bytes / (lookup_ms * 1e-3) / 1e9
-        dec_gbs = rows * (V * 4 + 4) / (decode_ms * 1e-3) / 1e9
+        alg_bytes, enc_gbs, dec_gbs = roofline_numbers(rows, V, encode_ms, decode_ms)
         line = {
-            "metric": METRIC, "value": world * rows * args.steps / (elapsed_ms * 1e-3), "unit": UNIT,
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": world * tokens_per_job * args.steps / (elapsed_ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32->u32/u64", "data": "synthetic", "config": workload_config(world),
-            "roofline": {"bound": "hbm", "kernel": "summary_kernel (fused softmax -> fixed-total quantisation -> clamp -> prefix sums; one HBM pass over the logits), timed through lac_cdf_lookup_f32 together with its pair_kernel ((lo, hi) of the coded symbol)",
-                         "achieved": look_gbs, "peak": peak, "unit": "GB/s", "frac": look_gbs / peak,
+            "roofline": {"bound": "hbm",
+                         "kernel": "summary_kernel (fused softmax -> fixed-total quantisation -> min-frequency clamp -> "
+                                   "segment prefix sums; the one HBM pass over the logits), timed through the whole "
+                                   "lac_ac_encode_logits_f32 call, i.e. together with encode_fused_kernel (symbol ranges + "
+                                   "range coder); the ncu launch list under profiles/ gives the split",
+                         "achieved": enc_gbs, "peak": peak, "unit": "GB/s", "frac": enc_gbs / peak,
                          "traffic": measured_traffic("summary_kernel", V, rows), "peak_source": peak_src,
                          "peak_note": "the peak is the copy-measured (read + write) figure; a read-only stream reaches 7.2-7.8 TB/s on this part (profiles/microbench/tma_stream_b200.txt), so frac may exceed 1",
                          "algorithmic_bytes_per_launch": alg_bytes,
-                         "ms_per_launch": lookup_ms,
-                         "decode": {"kernels": "dec_init + summary_kernel + decode_serial_kernel", "achieved": dec_gbs,
-                                    "frac": dec_gbs / peak, "ms_per_call": decode_ms},
-                         "coder_kernel_ms": coder_ms},
-            "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clk,
+                         "ms_per_launch": encode_ms,
+                         "decode": {"kernels": "summary_kernel + decode_serial_kernel (lac_ac_decode_logits_f32)",
+                                    "achieved": dec_gbs, "frac": dec_gbs / peak, "ms_per_call": decode_ms},
+                         "timed_over": f"{n_ev} jobs x {job.n_slices} slices, CUDA events around every call",
+                         "v128256": v128},
+            "e2e": e2e, "gpu_launches": job.launches * args.steps, "clocks": clk,
             "bits_per_token": bits_per_token,
         }
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline_leg()
+            cb = cpu_baseline_leg()
+            line["cpu_baseline"] = cb
+            line["bits_per_token_reference_literal"] = cb["bits_per_token"]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -340,8 +441,12 @@ def main():
     ap.add_argument("--vocab", type=int, default=VOCAB)
     ap.add_argument("--streams", type=int, default=STREAMS)
     ap.add_argument("--slice", type=int, default=SLICE)
+    ap.add_argument("--chunk-tokens", type=int, default=CHUNK_TOKENS)
+    ap.add_argument("--no-v128", action="store_true")
+    ap.add_argument("--v128-tokens", type=int, default=256)
+    ap.add_argument("--v128-jobs", type=int, default=4)
     args = ap.parse_args()
-    globals().update(VOCAB=args.vocab, STREAMS=args.streams, SLICE=args.slice)
+    globals().update(VOCAB=args.vocab, STREAMS=args.streams, SLICE=args.slice, CHUNK_TOKENS=args.chunk_tokens)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -12,10 +12,10 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "liblac_b200.so")
 
-LAC_OK, LAC_E_ARG, LAC_E_CUDA, LAC_E_CAP, LAC_E_SYMBOL = 0, -1, -2, -3, -4
-LAC_ST_CAP, LAC_ST_SYMBOL, LAC_ST_TABLE = 1, 2, 4
+LAC_OK, LAC_E_ARG, LAC_E_CUDA, LAC_E_CAP, LAC_E_SYMBOL, LAC_E_STREAM = 0, -1, -2, -3, -4, -5
+LAC_ST_CAP, LAC_ST_SYMBOL, LAC_ST_TABLE, LAC_ST_TRUNC = 1, 2, 4, 8
 LAC_F_WRAP64 = 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class LacError(RuntimeError):
@@ -44,17 +44,21 @@ SIGNATURES = {
     "lac_abi_version": [],
     "lac_last_error": [],
     "lac_device_info": [_p, _p, _p, _p],
-    "lac_cdf_build_f32": [_p, _i64, _i32, _i64, _p, _p],
-    "lac_cdf_lookup_f32": [_p, _i64, _i32, _i64, _p, _p, _p, _p],
+    "lac_workspace_bytes": [_i64, _i32],
+    "lac_cdf_build_f32": [_p, _i64, _i32, _i64, _p, _p, _i64, _p],
+    "lac_cdf_lookup_f32": [_p, _i64, _i32, _i64, _p, _p, _p, _p, _i64, _p],
     "lac_enc_init": [_p, _i64, _int, _p],
     "lac_dec_init": [_p, _i64, _int, _p, _p, _p],
     "lac_ac_encode_pairs": [_p, _i64, _i64, _i64, _i64, _p, _p, _p, _i64, _int, _int, _p],
     "lac_ac_encode_uniform": [_p, _i64, _i64, _i64, _p, _i32, _p, _p, _i64, _int, _int, _p],
     "lac_ac_decode_uniform": [_i64, _i64, _p, _i32, _p, _p, _p, _p, _i64, _int, _p],
-    "lac_ac_decode_logits_f32": [_p, _i64, _i64, _i64, _i64, _i32, _p, _p, _p, _p, _p, _i64, _int, _p],
-    "lac_ac_encode_tables": [_p, _i32, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _i64, _int, _int, _int, _p],
+    "lac_ac_encode_logits_f32": [_p, _i64, _i64, _i64, _i64, _i32, _p, _i64, _p, _p, _p, _i64, _int, _int, _p, _i64, _p],
+    "lac_ac_decode_logits_f32": [_p, _i64, _i64, _i64, _i64, _i32, _p, _p, _p, _p, _p, _i64, _int, _p, _i64, _p],
+    "lac_enc_status": [_p, _i64, _p, _p],
+    "lac_dec_status": [_p, _i64, _p, _p],
+    "lac_ac_encode_tables": [_p, _i32, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _p, _p, _p, _i64, _int, _int, _int, _p],
     "lac_ac_decode_tables": [_p, _i32, _i64, _i64, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i64, _int, _int, _p],
-    "lac_acs_encode_tables": [_p, _i32, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _i64, _int, _int, _p],
+    "lac_acs_encode_tables": [_p, _i32, _i64, _i64, _p, _i64, _i64, _i64, _p, _p, _p, _i64, _int, _int, _p],
     "lac_acs_decode_tables": [_p, _i32, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i64, _int, _p],
     "lac_encode_logits_host": [_p, _p, _i64, _i64, _i32, _p, _i64, _p, _int],
     "lac_decode_logits_host": [_p, _i64, _i64, _i32, _p, _p, _p, _int],
@@ -74,7 +78,8 @@ def lib():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = argtypes
-            fn.restype = C.c_char_p if name == "lac_last_error" else C.c_int
+            fn.restype = (C.c_char_p if name == "lac_last_error" else
+                          C.c_int64 if name == "lac_workspace_bytes" else C.c_int)
         if L.lac_abi_version() != ABI_VERSION:
             raise LacError(LAC_E_ARG, f"ABI version mismatch: library {L.lac_abi_version()}, binding {ABI_VERSION}")
         _lib = L

@@ -7,8 +7,10 @@ Conventions
 * uint32 values (LQ32 cumulative frequencies, pairs) are carried in torch.int32 tensors
   holding the same 32 bits; `u32(t)` widens them to int64 for arithmetic on the host side.
 * Bitstreams are MSB-first bytes, byte-for-byte what the reference's
-  bytes(group_bits(A_to_bin.bits(...))) (arith_code.py:347-358) / packbits
-  (arithmetic_coding.py:200-214) produce.
+  bytes(group_bits(A_to_bin.bits(...))) (arith_code.py:336-347) / packbits
+  (arithmetic_coding.py:212-225) produce.
+* Workspace: the logits-driven calls take an optional `Workspace` (device scratch for the row summaries); with one
+  they allocate nothing, which is what a per-token loop or a CUDA graph wants.
 """
 from __future__ import annotations
 
@@ -36,25 +38,42 @@ def _need_cuda(t: torch.Tensor, name: str, dtype=None):
         raise LacError(_ffi.LAC_E_ARG, f"{name} must be contiguous")
 
 
+class Workspace:
+    """Device scratch for the logits-driven calls, sized for `rows` logits rows per call (lac_workspace_bytes)."""
+
+    def __init__(self, rows: int, vocab: int, device="cuda"):
+        self.nbytes = int(lib().lac_workspace_bytes(int(rows), int(vocab)))
+        self.buf = torch.empty(max(self.nbytes, 16), dtype=torch.uint8, device=device)
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr()
+
+
+def _ws(ws: Optional["Workspace"]):
+    return (ws.ptr, ws.nbytes) if ws is not None else (None, 0)
+
+
 def u32(t: torch.Tensor) -> torch.Tensor:
     """int32-carried uint32 -> int64 values."""
     return t.to(torch.int64) & 0xFFFFFFFF
 
 
 # ------------------------------------------------------------------------------------ (a) CDF
-def cdf_build(logits: torch.Tensor) -> torch.Tensor:
+def cdf_build(logits: torch.Tensor, ws: Optional[Workspace] = None) -> torch.Tensor:
     """LQ32 exclusive cumulative table per row: int32-carried uint32 [rows, V]; total 2^32 implicit.
 
     Replaces Llama_AC.calc_dist (llama_compress.py:24-30) / ProbPredictor.calc_dist
-    (arith_code.py:120-126)."""
+    (arith_code.py:117-123)."""
     _need_cuda(logits, "logits", torch.float32)
     rows, V = logits.shape
     cum = torch.empty((rows, V), dtype=torch.int32, device=logits.device)
-    check(lib().lac_cdf_build_f32(logits.data_ptr(), rows, V, V, cum.data_ptr(), _cur_stream()))
+    check(lib().lac_cdf_build_f32(logits.data_ptr(), rows, V, V, cum.data_ptr(), *_ws(ws), _cur_stream()))
     return cum
 
 
-def cdf_lookup(logits: torch.Tensor, syms: torch.Tensor, status: Optional[torch.Tensor] = None) -> torch.Tensor:
+def cdf_lookup(logits: torch.Tensor, syms: torch.Tensor, status: Optional[torch.Tensor] = None,
+               ws: Optional[Workspace] = None) -> torch.Tensor:
     """(cum[sym], cum[sym+1]) per row, int32-carried uint32 [rows, 2]; hi == 0 means 2^32."""
     _need_cuda(logits, "logits", torch.float32)
     _need_cuda(syms, "syms", torch.int32)
@@ -63,7 +82,7 @@ def cdf_lookup(logits: torch.Tensor, syms: torch.Tensor, status: Optional[torch.
         raise LacError(_ffi.LAC_E_ARG, "syms must have one entry per logits row")
     pairs = torch.empty((rows, 2), dtype=torch.int32, device=logits.device)
     check(lib().lac_cdf_lookup_f32(logits.data_ptr(), rows, V, V, syms.data_ptr(), pairs.data_ptr(),
-                                   status.data_ptr() if status is not None else None, _cur_stream()))
+                                   status.data_ptr() if status is not None else None, *_ws(ws), _cur_stream()))
     return pairs
 
 
@@ -93,7 +112,7 @@ def _collect_streams(out: torch.Tensor, state: torch.Tensor) -> Tuple[List[bytes
 
 
 class StreamEncoder:
-    """n_streams independent A_to_bin coders (arith_code.py:147-231) living on the GPU.
+    """n_streams independent A_to_bin coders (arith_code.py:156-246) living on the GPU.
 
     Feed tokens in slices (state persists between calls), then finish()."""
 
@@ -122,11 +141,23 @@ class StreamEncoder:
         self.finished = self.finished or finish
 
     def encode_logits(self, logits: torch.Tensor, syms: torch.Tensor, ntok: Optional[torch.Tensor] = None,
-                      finish: bool = False):
-        """logits [n_streams, T, V] fp32, syms [n_streams, T] int32: fused CDF lookup, then the coder."""
+                      finish: bool = False, ws: Optional[Workspace] = None):
+        """logits [n_streams, T, V] fp32, syms [n_streams, T] int32: one pass over the logits (row summaries), then
+        ONE kernel that looks up the coded symbols' ranges and runs the coder (lac_ac_encode_logits_f32)."""
+        _need_cuda(logits, "logits", torch.float32)
+        _need_cuda(syms, "syms", torch.int32)
         S, T, V = logits.shape
-        pairs = cdf_lookup(logits.reshape(S * T, V), syms.reshape(S * T))
-        self.encode_pairs(pairs.view(S, T, 2), ntok, finish)
+        if S != self.n or tuple(syms.shape) != (S, T):
+            raise LacError(_ffi.LAC_E_ARG, "logits must be [n_streams, T, V] and syms [n_streams, T]")
+        check(lib().lac_ac_encode_logits_f32(logits.data_ptr(), S, T, T * V, V, V, syms.data_ptr(), T,
+                                             self._ntok(ntok), self.state.data_ptr(), self.out.data_ptr(), self.cap,
+                                             int(finish), self.prec, *_ws(ws), _cur_stream()))
+        self.finished = self.finished or finish
+
+    def encode_step(self, logits: torch.Tensor, syms: torch.Tensor, live: Optional[torch.Tensor] = None,
+                    ws: Optional[Workspace] = None):
+        """One model-in-the-loop step: logits [n_streams, V], syms [n_streams]; live [n_streams] int32 0 / 1."""
+        self.encode_logits(logits.unsqueeze(1), syms.unsqueeze(1), live, False, ws)
 
     def encode_tables(self, dist: torch.Tensor, syms: torch.Tensor, minp: torch.Tensor,
                       ntok: Optional[torch.Tensor] = None, finish: bool = False, wrap64: bool = False):
@@ -137,14 +168,14 @@ class StreamEncoder:
         _need_cuda(syms, "syms", torch.int32)
         S, T = syms.shape
         V, ss, ts, mss, mts = _table_strides(dist, minp, S, T)
-        check(lib().lac_ac_encode_tables(dist.data_ptr(), V, ss, ts, minp.data_ptr(), mss, mts, syms.data_ptr(), S, T,
+        check(lib().lac_ac_encode_tables(dist.data_ptr(), V, ss, ts, minp.data_ptr(), mss, mts, syms.data_ptr(), T, S, T,
                                          self._ntok(ntok), self.state.data_ptr(), self.out.data_ptr(), self.cap,
                                          int(finish), self.prec, _ffi.LAC_F_WRAP64 if wrap64 else 0, _cur_stream()))
         self.finished = self.finished or finish
 
     def encode_uniform(self, syms: torch.Tensor, n_symbols: int, ntok: Optional[torch.Tensor] = None,
                        finish: bool = False):
-        """The reference's uniform base class Predictor(n) (arith_code.py:63-74, floor-mapped ranges)."""
+        """The reference's uniform base class Predictor(n) (arith_code.py:64-74, floor-mapped ranges)."""
         _need_cuda(syms, "syms", torch.int32)
         S, T = syms.shape
         check(lib().lac_ac_encode_uniform(syms.data_ptr(), S, T, T, self._ntok(ntok), int(n_symbols),
@@ -161,7 +192,7 @@ class StreamEncoder:
         _need_cuda(syms, "syms", torch.int32)
         S, T = syms.shape
         V, ss, ts, _, _ = _table_strides(cdf, None, S, T)
-        check(lib().lac_acs_encode_tables(cdf.data_ptr(), V, ss, ts, syms.data_ptr(), S, T, self._ntok(ntok),
+        check(lib().lac_acs_encode_tables(cdf.data_ptr(), V, ss, ts, syms.data_ptr(), T, S, T, self._ntok(ntok),
                                           self.state.data_ptr(), self.out.data_ptr(), self.cap,
                                           2 if finish == "safe" else int(bool(finish)), self.prec, _cur_stream()))
         self.finished = self.finished or bool(finish)
@@ -215,7 +246,7 @@ def pack_streams(streams: Sequence[bytes], device="cuda") -> Tuple[torch.Tensor,
 
 
 class StreamDecoder:
-    """n_streams independent A_from_bin decoders (arith_code.py:233-345) on the GPU, decoding a
+    """n_streams independent A_from_bin decoders (arith_code.py:248-334) on the GPU, decoding a
     known number of tokens (the reference has no length framing; the container supplies it)."""
 
     def __init__(self, streams: Sequence[bytes], prec: int = DEFAULT_PREC, device="cuda"):
@@ -226,22 +257,37 @@ class StreamDecoder:
         check(lib().lac_dec_init(self.state.data_ptr(), self.n, self.prec, self.bytes.data_ptr(),
                                  self.offsets.data_ptr(), _cur_stream()))
 
-    def decode_logits(self, logits: torch.Tensor, ntok: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """logits [n_streams, T, V] fp32 -> symbols int32 [n_streams, T] (fused CDF rebuild + search + update)."""
+    def decode_logits(self, logits: torch.Tensor, ntok: Optional[torch.Tensor] = None,
+                      ws: Optional[Workspace] = None, out: Optional[torch.Tensor] = None,
+                      check_status: bool = True) -> torch.Tensor:
+        """logits [n_streams, T, V] fp32 -> symbols int32 [n_streams, T] (row summaries, then search + update).
+        Raises LacError(LAC_E_STREAM) for a truncated / foreign stream unless check_status=False (a per-token loop
+        checks once at the end with status())."""
         _need_cuda(logits, "logits", torch.float32)
         S, T, V = logits.shape
         if S != self.n:
             raise LacError(_ffi.LAC_E_ARG, "logits must be [n_streams, T, V]")
-        syms = torch.zeros((S, T), dtype=torch.int32, device=self.device)
+        syms = out if out is not None else torch.zeros((S, T), dtype=torch.int32, device=self.device)
         check(lib().lac_ac_decode_logits_f32(logits.data_ptr(), S, T, T * V, V, V,
                                              ntok.data_ptr() if ntok is not None else None, self.state.data_ptr(),
-                                             self.bytes.data_ptr(), self.offsets.data_ptr(), syms.data_ptr(), T,
-                                             self.prec, _cur_stream()))
+                                             self.bytes.data_ptr(), self.offsets.data_ptr(), syms.data_ptr(),
+                                             syms.stride(0), self.prec, *_ws(ws), _cur_stream()))
+        if check_status:
+            self._check_status()
         return syms
 
-    def decode_step(self, logits: torch.Tensor) -> torch.Tensor:
-        """One model-in-the-loop step: logits [n_streams, V] -> symbols [n_streams]."""
-        return self.decode_logits(logits.unsqueeze(1)).squeeze(1)
+    def decode_step(self, logits: torch.Tensor, live: Optional[torch.Tensor] = None, ws: Optional[Workspace] = None,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One model-in-the-loop step: logits [n_streams, V] -> symbols [n_streams] (status checked by the caller
+        at the end of the loop: status())."""
+        o = out.unsqueeze(1) if out is not None else None
+        return self.decode_logits(logits.unsqueeze(1), live, ws, o, check_status=False).squeeze(1)
+
+    def status(self) -> int:
+        """OR of the streams' status words (one 4-byte read)."""
+        flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        check(lib().lac_dec_status(self.state.data_ptr(), self.n, flag.data_ptr(), _cur_stream()))
+        return int(flag.item()) & 0xFFFFFFFF
 
     def decode_tables(self, dist: torch.Tensor, minp: torch.Tensor, T: int, ntok: Optional[torch.Tensor] = None,
                       wrap64: bool = False) -> torch.Tensor:
@@ -277,10 +323,15 @@ class StreamDecoder:
         return syms
 
     def _check_status(self):
+        if self.status() == 0:
+            return
         st = self.state.cpu().numpy().view(np.uint8).reshape(-1, _ffi.DEC_STATE_BYTES)
         status = st[:, 32:36].copy().view(np.uint32).reshape(-1)
-        if status.any():
-            raise LacError(_ffi.LAC_E_ARG, f"unusable table on streams {np.nonzero(status)[0][:8].tolist()}")
+        if (status & _ffi.LAC_ST_TRUNC).any():
+            bad = np.nonzero(status & _ffi.LAC_ST_TRUNC)[0][:8].tolist()
+            raise LacError(_ffi.LAC_E_STREAM, f"truncated or foreign bitstream on streams {bad} "
+                                              "(more bits consumed than the stream holds)")
+        raise LacError(_ffi.LAC_E_ARG, f"unusable table on streams {np.nonzero(status)[0][:8].tolist()}")
 
 
 # ------------------------------------------------------------------------------------ host-buffer calls

@@ -1,16 +1,16 @@
 // coder.cuh -- range-narrowing state machines of the reference, device side.
 //
-//   arith_code.py:147-201    A_to_bin   (receive_symbol, decide_bit/emit_bit, flush)
-//   arith_code.py:233-306    A_from_bin (as a value-tracking decoder: the symbol emitted is
+//   arith_code.py:156-246    A_to_bin   (receive_symbol, decide_bit/emit_bit, flush)
+//   arith_code.py:248-334    A_from_bin (as a value-tracking decoder: the symbol emitted is
 //                            always the one whose range contains the stream's value)
-//   arithmetic_coding.py:129-196  Region.step/emit + CarryBuffer (same renormalisation,
+//   arithmetic_coding.py:129-208  Region.step/emit + CarryBuffer (same renormalisation,
 //                            floor-mapped sub-intervals, middle-third flush)
 //
 // The reference emits one bit per loop iteration; here the k renormalisation bits of a
 // token are produced at once: after k doublings l_k = (l_0 mod 2^(P-k)) * 2^k and the bits
 // are E = floor(l_0 / 2^(P-k)), which may carry (E >= 2^k) into bits already written, or
 // borrow (E < 0, flush only).  BitWriter resolves that exactly like A_to_bin.encode's
-// r = (r << 1) + v (arith_code.py:194-201) / CarryBuffer.add (arithmetic_coding.py:186-190).
+// r = (r << 1) + v (arith_code.py:208-215) / CarryBuffer.add (arithmetic_coding.py:197-201).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -38,10 +38,14 @@ struct BitWriter {
         nacc = (int)(nb & 7);
         acc = 0;
         status = 0;
-        if (nacc) acc = out[nb >> 3] >> (8 - nacc);
+        if (nacc && (nb >> 3) < cap) acc = out[nb >> 3] >> (8 - nacc);
     }
     // add E (signed, |E| < 2^(k+3)) as the next k bits, k <= 40
     __device__ void append_small(int64_t E, int k) {
+        if (status & LAC_ST_CAP) {  // a truncated stream is never touched again (no ripple into foreign bytes)
+            nbits += (uint64_t)k;
+            return;
+        }
         int64_t a = (acc << k) + E;
         int n = nacc + k;
         int64_t c = a >> n;  // carry (>0) or borrow (<0) into bytes already stored
@@ -75,10 +79,112 @@ struct BitWriter {
     // store the partial byte zero-padded (group_bits' tail, arith_code.py:354-357); the bits
     // stay accounted in nbits so a later open() resumes mid-byte.
     __device__ void close() {
-        if (nacc) {
+        if (nacc && !(status & LAC_ST_CAP)) {
             uint64_t pos = nbits >> 3;
             if (pos < cap) out[pos] = (uint8_t)(acc << (8 - nacc));
             else status |= LAC_ST_CAP;
+        }
+    }
+};
+
+// ---------------------------------------------------------------- staged bit output (fused encoder)
+// Same arithmetic as BitWriter, but complete bytes go to a per-stream shared-memory stage that the whole block
+// flushes to global memory in coalesced pieces after the coding phase; carries and borrows ripple through the
+// stage first and only reach global memory (read-modify-write of bytes flushed by an earlier pass) in the rare case
+// that they run past it.  The caller flushes stage[0 .. fill) to out[base .. base + fill) and calls flushed().
+struct StagedWriter {
+    uint8_t* out;    // the stream's region in global memory
+    uint8_t* stage;  // shared memory, kStage bytes
+    uint64_t cap;    // bytes of the stream's region
+    uint64_t nbits;  // bits emitted so far, including the nacc bits still in acc
+    uint64_t base;   // stream byte index of stage[0]
+    int64_t acc;     // value of the last nacc bits
+    int nacc;        // 0..7 between calls
+    int fill;        // staged bytes
+    int tail;        // 1: stage[fill] holds the zero-padded partial byte (flush fill + tail bytes)
+    uint32_t status;
+    static constexpr int kStage = 160;
+
+    __device__ void open(uint8_t* o, uint8_t* stg, uint64_t c, uint64_t nb, uint32_t st) {
+        out = o;
+        stage = stg;
+        cap = c;
+        nbits = nb;
+        nacc = (int)(nb & 7);
+        base = nb >> 3;
+        fill = 0;
+        tail = 0;
+        acc = 0;
+        status = st;
+        if (nacc && base < cap) acc = out[base] >> (8 - nacc);
+    }
+    __device__ void spill() {  // stage full inside a pass (k near 60 for many tokens in a row): the thread writes it out
+        for (int i = 0; i < fill; i++) out[base + (uint64_t)i] = stage[i];
+        base += (uint64_t)fill;
+        fill = 0;
+    }
+    __device__ void flushed() {
+        base += (uint64_t)fill;
+        fill = 0;
+    }
+    __device__ void append_small(int64_t E, int k) {  // add E (signed, |E| < 2^(k+3)) as the next k bits, k <= 40
+        if (status & LAC_ST_CAP) {  // a truncated stream is never touched again
+            nbits += (uint64_t)k;
+            return;
+        }
+        int64_t a = (acc << k) + E;
+        int n = nacc + k;
+        int64_t c = a >> n;  // carry (>0) or borrow (<0) into bytes already produced
+        a -= c << n;
+        if (c != 0) {
+            int i = fill;
+            while (c != 0 && i > 0) {
+                i--;
+                const int64_t t = (int64_t)stage[i] + c;
+                stage[i] = (uint8_t)(t & 255);
+                c = t >> 8;
+            }
+            uint64_t g = base;
+            while (c != 0 && g > 0) {
+                g--;
+                const int64_t t = (int64_t)out[g] + c;
+                out[g] = (uint8_t)(t & 255);
+                c = t >> 8;
+            }
+        }
+        nbits += (uint64_t)k;
+        while (n >= 8) {
+            n -= 8;
+            if (base + (uint64_t)fill < cap) {
+                if (fill == kStage) spill();
+                stage[fill++] = (uint8_t)((a >> n) & 255);
+            } else {
+                status |= LAC_ST_CAP;
+            }
+        }
+        acc = a & ((1ll << n) - 1);
+        nacc = n;
+    }
+    __device__ void append(int64_t E, int k) {
+        if (k > 32) {
+            const int k2 = k - 32;
+            append_small(E >> k2, 32);  // arithmetic shift keeps carries / borrows in the high part
+            append_small(E & ((1ll << k2) - 1), k2);
+        } else if (k > 0 || E != 0) {
+            append_small(E, k);
+        }
+    }
+    // the partial byte, zero-padded (group_bits' tail, arith_code.py:345-348), goes behind the staged bytes; it stays
+    // accounted in nbits only, so a later open() resumes mid-byte
+    __device__ void close() {
+        if (nacc && !(status & LAC_ST_CAP)) {
+            if (base + (uint64_t)fill < cap) {
+                if (fill == kStage) spill();
+                stage[fill] = (uint8_t)(acc << (8 - nacc));
+                tail = 1;
+            } else {
+                status |= LAC_ST_CAP;
+            }
         }
     }
 };
@@ -138,7 +244,8 @@ __device__ __forceinline__ int64_t region_overlap(int64_t a, int64_t b, int64_t 
 }
 
 // A_to_bin.flush (arith_code.py:185-194), literal: at most P + 2 iterations.
-__device__ inline void ac_flush(int64_t& l, int64_t& h, int P, BitWriter& bw) {
+template <class Writer>
+__device__ inline void ac_flush(int64_t& l, int64_t& h, int P, Writer& bw) {
     const int64_t denom = 1ll << P, decision = 1ll << (P - 1);
     while (l > 0 || h + 1 < denom) {
         int64_t b = l >> (P - 1);  // floor(l / decision), l may be negative

@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 
 #include "coder.cuh"
+#include "launch.h"
+#include "rowsum.cuh"
 
 namespace lac {
 
@@ -72,9 +74,13 @@ __global__ void encode_pairs_kernel(const uint2* __restrict__ pairs, int64_t n_s
 #pragma unroll
         for (int j = 0; j < kBatch; j++) {
             if (t0 + j < Ts && !bad) {
-                if (pr[j].y != 0 && pr[j].y <= pr[j].x) {  // zero-width symbol: the reference would never terminate
-                    bw.status |= LAC_ST_TABLE;
+                if (pr[j].y != 0 && pr[j].y <= pr[j].x) {
+                    // the lookup's sentinel for a symbol outside [0, V) (the reference raises "unknown symbol",
+                    // arith_code.py:104-105), or a zero-width symbol (the reference would never terminate)
+                    bw.status |= (pr[j].x == 0xFFFFFFFFu && pr[j].y == 0xFFFFFFFFu) ? LAC_ST_SYMBOL : LAC_ST_TABLE;
                     bad = true;
+                } else if (bw.status & LAC_ST_CAP) {
+                    bad = true;  // truncated: stop coding this stream
                 } else {
                     coder::ac_narrow32(l, h, pr[j].x, pr[j].y);
                     int k = coder::renorm_count((uint64_t)(h - l + 1), P);
@@ -84,12 +90,130 @@ __global__ void encode_pairs_kernel(const uint2* __restrict__ pairs, int64_t n_s
             }
         }
     }
-    if (finish && !(bw.status & LAC_ST_TABLE)) coder::ac_flush(l, h, P, bw);
+    if (finish && !(bw.status & (LAC_ST_TABLE | LAC_ST_SYMBOL | LAC_ST_CAP))) coder::ac_flush(l, h, P, bw);
     bw.close();
     state[s].low = l;
     state[s].high = h;
     state[s].nbits = bw.nbits;
     state[s].status = bw.status;
+}
+
+// ------------------------------------------------------------------ fused encoder (second pass of the encode side)
+// One block per group of `spb` streams, 8 warps.  Per batch of `tb` tokens:
+//   lookup  the warps share the batch's spb * tb rows: symbol_to_range from the row summary + the symbol's segment
+//           (rowsum.cuh: 32 lanes per row, loads of a row issued together) -> (lo, hi) pairs in shared memory
+//   code    thread i < spb runs A_to_bin (arith_code.py:169-202) over its stream's pairs, low / high in registers,
+//           the k renormalisation bits of a token appended at once into the stream's shared-memory stage
+//           (carries resolved there, coder.cuh:StagedWriter)
+//   flush   every warp copies a stream's staged bytes to its global buffer (warp-wide coalesced stores)
+// The pairs never go to global memory and there is one launch per call: the model-in-the-loop step (T = 1) is
+// summary_kernel + this kernel.
+struct EncParams {
+    const float* base;
+    int64_t n_streams, T, so, st;
+    const int32_t* syms;
+    int64_t sym_stride;
+    const int32_t* ntok;  // per stream: tokens present counted from t0 tokens before `base` (nullptr: T everywhere)
+    int64_t t0;
+    const uint64_t* summ;
+    lac_enc_state* state;
+    uint8_t* out;
+    int64_t out_stride;
+    int V, P, finish, spb, tb;
+};
+constexpr int kEncWarps = 8;
+constexpr int kEncRows = 32;  // rows (pairs) per batch and block: spb * tb <= kEncRows
+constexpr int kEncMaxSpb = 16;
+
+template <int VEC, int CL>
+__global__ void __launch_bounds__(kEncWarps * 32)
+encode_fused_kernel(const __grid_constant__ EncParams ep) {
+    __shared__ uint2 s_pairs[kEncRows];
+    __shared__ uint8_t s_stage[kEncMaxSpb][coder::StagedWriter::kStage + 1];
+    __shared__ unsigned long long s_base[kEncMaxSpb];
+    __shared__ int s_fill[kEncMaxSpb];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t s0 = (int64_t)blockIdx.x * ep.spb;
+    const int ns = (int)min((int64_t)ep.spb, ep.n_streams - s0);  // streams of this block
+    // coder threads: state in registers for the whole call
+    const bool is_coder = threadIdx.x < ns;
+    const int64_t sc = s0 + threadIdx.x;
+    int64_t l = 0, h = 0;
+    int my_tokens = 0;
+    coder::StagedWriter bw;
+    if (is_coder) {
+        l = ep.state[sc].low;
+        h = ep.state[sc].high;
+        bw.open(ep.out + sc * ep.out_stride, s_stage[threadIdx.x], (uint64_t)ep.out_stride, ep.state[sc].nbits,
+                ep.state[sc].status);
+        int64_t n = ep.ntok ? (int64_t)ep.ntok[sc] - ep.t0 : ep.T;
+        my_tokens = (int)(n < 0 ? 0 : (n > ep.T ? ep.T : n));
+    }
+    bool dead = false;  // coder thread: stream stopped (bad symbol / table, capacity)
+    int64_t tb0 = 0;
+    do {  // (a call with T = 0 still runs the flush / close of the last batch)
+        const int nt = (int)min((int64_t)ep.tb, ep.T - tb0);
+        // ---- lookup: row j of the batch = (stream j / nt, token tb0 + j % nt)
+        for (int j = warp; j < ns * nt; j += kEncWarps) {
+            const int si = j / nt, ti = j - si * nt;
+            const int64_t s = s0 + si, t = tb0 + ti;
+            const int64_t n = ep.ntok ? (int64_t)ep.ntok[s] - ep.t0 : ep.T;
+            if (t >= n) continue;  // past the end of a ragged stream (warp-uniform)
+            const int sym = __ldg(ep.syms + s * ep.sym_stride + t);
+            uint2 pr = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);  // symbol outside [0, V)
+            if (sym >= 0 && sym < ep.V)
+                pr = warp_symbol_range<VEC, CL>(ep.base + s * ep.so + t * ep.st, ep.V,
+                                                ep.summ + (s * ep.T + t) * (32 * CL), sym, lane);
+            if (lane == 0) s_pairs[j] = pr;
+        }
+        __syncthreads();
+        // ---- code
+        if (is_coder && !dead) {
+            const int n_here = min(nt, my_tokens - (int)tb0);
+            for (int ti = 0; ti < n_here; ti++) {
+                const uint2 pr = s_pairs[threadIdx.x * nt + ti];
+                if (pr.y != 0 && pr.y <= pr.x) {
+                    // the lookup's sentinel for an unknown symbol (the reference raises, arith_code.py:100-101), or a
+                    // zero-width symbol (the reference would never terminate)
+                    bw.status |= (pr.x == 0xFFFFFFFFu && pr.y == 0xFFFFFFFFu) ? LAC_ST_SYMBOL : LAC_ST_TABLE;
+                    dead = true;
+                    break;
+                }
+                coder::ac_narrow32(l, h, pr.x, pr.y);
+                const int k = coder::renorm_count((uint64_t)(h - l + 1), ep.P);
+                const int64_t E = coder::renorm_apply(l, h, ep.P, k);
+                bw.append(E, k);
+                if (bw.status & LAC_ST_CAP) {
+                    dead = true;
+                    break;
+                }
+            }
+            if (tb0 + nt >= ep.T) {  // last batch of the call
+                if (ep.finish && !(bw.status & (LAC_ST_TABLE | LAC_ST_SYMBOL | LAC_ST_CAP))) coder::ac_flush(l, h, ep.P, bw);
+                bw.close();
+            }
+        }
+        if (is_coder) {
+            s_base[threadIdx.x] = bw.base;
+            s_fill[threadIdx.x] = bw.fill + bw.tail;
+        }
+        __syncthreads();
+        // ---- flush: warp w copies the staged bytes of streams w, w + 8, ...
+        for (int si = warp; si < ns; si += kEncWarps) {
+            uint8_t* dst = ep.out + (s0 + si) * ep.out_stride + s_base[si];
+            const int nb = s_fill[si];
+            for (int i = lane; i < nb; i += 32) dst[i] = s_stage[si][i];
+        }
+        if (is_coder) bw.flushed();
+        __syncthreads();  // the stage and the pairs are reused by the next batch
+        tb0 += ep.tb;
+    } while (tb0 < ep.T);
+    if (is_coder) {
+        ep.state[sc].low = l;
+        ep.state[sc].high = h;
+        ep.state[sc].nbits = bw.nbits;
+        ep.state[sc].status = bw.status;
+    }
 }
 
 // ------------------------------------------------------------------ uniform Predictor(n) (arith_code.py:63-74)
@@ -123,8 +247,9 @@ __global__ void uniform_encode_kernel(const int32_t* __restrict__ syms, int64_t 
         int k = coder::renorm_count((uint64_t)(h - l + 1), P);
         int64_t E = coder::renorm_apply(l, h, P, k);
         bw.append(E, k);
+        if (bw.status & LAC_ST_CAP) break;
     }
-    if (finish && !(bw.status & (LAC_ST_TABLE | LAC_ST_SYMBOL))) coder::ac_flush(l, h, P, bw);
+    if (finish && !(bw.status & (LAC_ST_TABLE | LAC_ST_SYMBOL | LAC_ST_CAP))) coder::ac_flush(l, h, P, bw);
     bw.close();
     state[s].low = l;
     state[s].high = h;
@@ -300,10 +425,10 @@ __device__ __forceinline__ TableCtx table_ctx(const int64_t* dist, int V, int64_
 // ------------------------------------------------------------------ A_to_bin on tables
 __global__ void ac_tables_encode_kernel(const int64_t* __restrict__ dist, int V, int64_t ss, int64_t ts,
                                         const int64_t* __restrict__ minp, int64_t mss, int64_t mts,
-                                        const int32_t* __restrict__ syms, int64_t n_streams, int64_t T,
-                                        const int32_t* __restrict__ ntok, lac_enc_state* __restrict__ state,
-                                        uint8_t* __restrict__ out, int64_t out_stride, int finish, int P,
-                                        int flags) {
+                                        const int32_t* __restrict__ syms, int64_t sym_stride, int64_t n_streams,
+                                        int64_t T, const int32_t* __restrict__ ntok,
+                                        lac_enc_state* __restrict__ state, uint8_t* __restrict__ out,
+                                        int64_t out_stride, int finish, int P, int flags) {
     const int lane = threadIdx.x & 31;
     int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (s >= n_streams) return;
@@ -313,7 +438,7 @@ __global__ void ac_tables_encode_kernel(const int64_t* __restrict__ dist, int V,
     bw.status = state[s].status;
     const int64_t Ts = ntok ? (int64_t)ntok[s] : T;
     for (int64_t t = 0; t < Ts; t++) {
-        const int sym = syms[s * T + t];
+        const int sym = syms[s * sym_stride + t];
         if (sym < 0 || sym >= V) {
             bw.status |= LAC_ST_SYMBOL;
             break;
@@ -329,9 +454,10 @@ __global__ void ac_tables_encode_kernel(const int64_t* __restrict__ dist, int V,
         int k = coder::renorm_count((uint64_t)(h - l + 1), P);
         int64_t E = coder::renorm_apply(l, h, P, k);
         if (lane == 0) bw.append(E, k);
+        if (__shfl_sync(0xffffffffu, bw.status, 0) & LAC_ST_CAP) break;
     }
     if (lane == 0) {
-        if (finish && !(bw.status & (LAC_ST_TABLE | LAC_ST_SYMBOL))) coder::ac_flush(l, h, P, bw);
+        if (finish && !(bw.status & (LAC_ST_TABLE | LAC_ST_SYMBOL | LAC_ST_CAP))) coder::ac_flush(l, h, P, bw);
         bw.close();
         state[s].low = l;
         state[s].high = h;
@@ -384,9 +510,10 @@ __global__ void ac_tables_decode_kernel(const int64_t* __restrict__ dist, int V,
 
 // ------------------------------------------------------------------ ACSampler on tables
 __global__ void acs_tables_encode_kernel(const uint64_t* __restrict__ cdf, int V, int64_t ss, int64_t ts,
-                                         const int32_t* __restrict__ syms, int64_t n_streams, int64_t T,
-                                         const int32_t* __restrict__ ntok, lac_enc_state* __restrict__ state,
-                                         uint8_t* __restrict__ out, int64_t out_stride, int finish, int P) {
+                                         const int32_t* __restrict__ syms, int64_t sym_stride, int64_t n_streams,
+                                         int64_t T, const int32_t* __restrict__ ntok,
+                                         lac_enc_state* __restrict__ state, uint8_t* __restrict__ out,
+                                         int64_t out_stride, int finish, int P) {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= n_streams) return;
     int64_t low = state[s].low, high = state[s].high;
@@ -395,7 +522,7 @@ __global__ void acs_tables_encode_kernel(const uint64_t* __restrict__ cdf, int V
     bw.status = state[s].status;
     const int64_t Ts = ntok ? (int64_t)ntok[s] : T;
     for (int64_t t = 0; t < Ts; t++) {
-        const int tok = syms[s * T + t];
+        const int tok = syms[s * sym_stride + t];
         if (tok < 0 || tok >= V) {
             bw.status |= LAC_ST_SYMBOL;
             break;
@@ -414,8 +541,9 @@ __global__ void acs_tables_encode_kernel(const uint64_t* __restrict__ cdf, int V
         }
         int k = coder::renorm_count((uint64_t)(high - low + 1), P);
         bw.append(coder::renorm_apply(low, high, P, k), k);
+        if (bw.status & LAC_ST_CAP) break;
     }
-    if (finish == 1 && !(bw.status & (LAC_ST_TABLE | LAC_ST_SYMBOL))) {
+    if (finish == 1 && !(bw.status & (LAC_ST_TABLE | LAC_ST_SYMBOL | LAC_ST_CAP))) {
         // flush_compress, arithmetic_coding.py:52-58: step(1, 2, 3), drain the carry buffer, reset.
         // Bit-exact with the reference, but the bits do not pin the final region (DESIGN.md
         // section 6): the last tokens may be undecodable by ANY decoder.
@@ -424,7 +552,7 @@ __global__ void acs_tables_encode_kernel(const uint64_t* __restrict__ cdf, int V
         bw.append(coder::renorm_apply(low, high, P, k), k);
         low = 0;
         high = (1ll << P) - 1;
-    } else if (finish == 2 && !(bw.status & (LAC_ST_TABLE | LAC_ST_SYMBOL))) {
+    } else if (finish == 2 && !(bw.status & (LAC_ST_TABLE | LAC_ST_SYMBOL | LAC_ST_CAP))) {
         // safe termination: shortest bit string whose every continuation stays inside [low, high]
         // (A_to_bin.flush, arith_code.py:185-194) -- always decodable
         coder::ac_flush(low, high, P, bw);
@@ -487,6 +615,24 @@ __global__ void acs_tables_decode_kernel(const uint64_t* __restrict__ cdf, int V
     }
 }
 
+// ------------------------------------------------------------------ status collection
+__global__ void status_or_kernel(const uint32_t* __restrict__ state, int64_t n, int stride_words, int status_word,
+                                 uint32_t* __restrict__ d_or) {
+    uint32_t v = 0;
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x)
+        v |= state[s * stride_words + status_word];
+    v = __reduce_or_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v) atomicOr(d_or, v);
+}
+cudaError_t launch_status_or(const void* state, int64_t n, int stride_words, int status_word, uint32_t* d_or,
+                             cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(d_or, 0, 4, st);
+    if (e != cudaSuccess || n == 0) return e;
+    const unsigned blocks = (unsigned)((n + 255) / 256 > 1024 ? 1024 : (n + 255) / 256);
+    status_or_kernel<<<blocks, 256, 0, st>>>((const uint32_t*)state, n, stride_words, status_word, d_or);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ launchers
 cudaError_t launch_enc_init(lac_enc_state* state, int64_t n, int P, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
@@ -501,10 +647,69 @@ cudaError_t launch_encode_pairs(const uint32_t* pairs, int64_t n, int64_t T, int
     // Each thread is a long dependent chain with data-dependent inner loops (bits per token differ per stream),
     // so few streams per warp (less divergence) on many SMs (more schedulers) beat dense blocks.
     // Measured (1024 streams x 16 tokens): 32 threads per block 22 us, 8: 18 us, 2: 15 us.
-    static const int tpb = getenv("LAC_CODER_TPB") ? atoi(getenv("LAC_CODER_TPB")) : 2;
+    static const int tpb_env = getenv("LAC_CODER_TPB") ? atoi(getenv("LAC_CODER_TPB")) : 2;
+    const int tpb = tpb_env < 1 ? 1 : (tpb_env > 1024 ? 1024 : tpb_env);
     encode_pairs_kernel<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, st>>>(reinterpret_cast<const uint2*>(pairs), n, T, ss,
                                                                   ts, ntok, state, out, out_stride, finish, P);
     return cudaGetLastError();
+}
+
+// lac_ac_encode_logits_f32: per token chunk (the summary scratch bounds it) summary pass + fused encoder.
+cudaError_t launch_encode_logits(const float* logits, int64_t n, int64_t T, int64_t ss, int64_t ts, int V,
+                                 const int32_t* syms, int64_t sym_stride, const int32_t* ntok, lac_enc_state* state,
+                                 uint8_t* out, int64_t out_stride, int finish, int P, void* ws, size_t ws_bytes,
+                                 cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    int parts = 1;
+    const int path = path_for(logits, V, ss, ts, &parts);
+    if (path < 0) return cudaErrorInvalidValue;
+    const int64_t Tn = T < 1 ? 1 : T;
+    int64_t tc = summ_rows_for(n * Tn, parts, ws, ws_bytes) / n;
+    tc = tc < 1 ? 1 : (tc > Tn ? Tn : tc);
+    Scratch sc;
+    cudaError_t e = scratch_get(&sc, summ_bytes(n * tc, parts), ws, ws_bytes, st);
+    if (e != cudaSuccess) return e;
+    for (int64_t t0 = 0; (t0 < T || (T == 0 && t0 == 0)) && e == cudaSuccess; t0 += tc) {
+        const int64_t tn = T - t0 < tc ? T - t0 : tc;
+        const float* base = logits + t0 * ts;
+        if (tn > 0) e = launch_summary(base, n, tn, ss, ts, V, parts, path, 0, (uint64_t*)sc.p, st);
+        if (e != cudaSuccess) break;
+        EncParams ep;
+        ep.base = base;
+        ep.n_streams = n;
+        ep.T = tn;
+        ep.so = ss;
+        ep.st = ts;
+        ep.syms = syms + t0;
+        ep.sym_stride = sym_stride;
+        ep.ntok = ntok;
+        ep.t0 = t0;
+        ep.summ = (const uint64_t*)sc.p;
+        ep.state = state;
+        ep.out = out;
+        ep.out_stride = out_stride;
+        ep.V = V;
+        ep.P = P;
+        ep.finish = (finish && t0 + tn >= T) ? 1 : 0;
+        // streams per block and tokens per batch: one stream per block for slices of >= 16 tokens (two rows per warp
+        // and batch), more streams per block for shorter calls so that every warp still has a row (T = 1: 8 streams)
+        ep.tb = (int)(tn >= 16 ? 16 : (tn < 1 ? 1 : tn));
+        ep.spb = tn >= 16 ? 1 : (kEncRows / 2 / ep.tb < 1 ? 1 : kEncRows / 2 / ep.tb);
+        if (ep.spb > 8) ep.spb = 8;
+        if (tn == 0) {  // flush-only call: as many streams per block as the stage allows
+            ep.spb = kEncMaxSpb;
+        }
+        const unsigned blocks = (unsigned)((n + ep.spb - 1) / ep.spb);
+#define LAC_ENC(CL_)                                                             \
+    if (path == 0) encode_fused_kernel<1, CL_><<<blocks, kEncWarps * 32, 0, st>>>(ep); \
+    else encode_fused_kernel<4, CL_><<<blocks, kEncWarps * 32, 0, st>>>(ep)
+        LAC_BY_PARTS(parts, LAC_ENC)
+#undef LAC_ENC
+        e = cudaGetLastError();
+        if (T == 0) break;
+    }
+    const cudaError_t ef = scratch_put(&sc, st);
+    return e != cudaSuccess ? e : ef;
 }
 
 cudaError_t launch_uniform_encode(const int32_t* syms, int64_t n, int64_t T, int64_t sym_stride, const int32_t* ntok,
@@ -526,12 +731,12 @@ cudaError_t launch_uniform_decode(int64_t n, int64_t T, const int32_t* ntok, int
 }
 
 cudaError_t launch_ac_tables_encode(const int64_t* dist, int V, int64_t ss, int64_t ts, const int64_t* minp,
-                                    int64_t mss, int64_t mts, const int32_t* syms, int64_t n, int64_t T,
-                                    const int32_t* ntok, lac_enc_state* state, uint8_t* out, int64_t out_stride,
-                                    int finish, int P, int flags, cudaStream_t st) {
+                                    int64_t mss, int64_t mts, const int32_t* syms, int64_t sym_stride, int64_t n,
+                                    int64_t T, const int32_t* ntok, lac_enc_state* state, uint8_t* out,
+                                    int64_t out_stride, int finish, int P, int flags, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    ac_tables_encode_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(dist, V, ss, ts, minp, mss, mts, syms, n, T,
-                                                                    ntok, state, out, out_stride, finish, P, flags);
+    ac_tables_encode_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(dist, V, ss, ts, minp, mss, mts, syms, sym_stride, n,
+                                                                    T, ntok, state, out, out_stride, finish, P, flags);
     return cudaGetLastError();
 }
 
@@ -547,11 +752,12 @@ cudaError_t launch_ac_tables_decode(const int64_t* dist, int V, int64_t ss, int6
 }
 
 cudaError_t launch_acs_tables_encode(const uint64_t* cdf, int V, int64_t ss, int64_t ts, const int32_t* syms,
-                                     int64_t n, int64_t T, const int32_t* ntok, lac_enc_state* state,
-                                     uint8_t* out, int64_t out_stride, int finish, int P, cudaStream_t st) {
+                                     int64_t sym_stride, int64_t n, int64_t T, const int32_t* ntok,
+                                     lac_enc_state* state, uint8_t* out, int64_t out_stride, int finish, int P,
+                                     cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    acs_tables_encode_kernel<<<(unsigned)((n + 31) / 32), 32, 0, st>>>(cdf, V, ss, ts, syms, n, T, ntok, state, out,
-                                                                      out_stride, finish, P);
+    acs_tables_encode_kernel<<<(unsigned)((n + 31) / 32), 32, 0, st>>>(cdf, V, ss, ts, syms, sym_stride, n, T, ntok,
+                                                                      state, out, out_stride, finish, P);
     return cudaGetLastError();
 }
 

@@ -102,6 +102,8 @@ class LlamaCompressor:
 
     def compress(self, tokens) -> bytes:
         toks = np.ascontiguousarray(tokens, dtype=np.int32)
+        if toks.size and (int(toks.min()) < 0 or int(toks.max()) >= self.vocab):
+            raise AssertionError("unknown symbol", int(toks.max() if toks.max() >= self.vocab else toks.min()))  # arith_code.py:104-105
         n_chunks = (len(toks) + self.chunk - 1) // self.chunk
         padded = np.zeros(n_chunks * self.chunk, dtype=np.int32)
         padded[: len(toks)] = toks

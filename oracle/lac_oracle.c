@@ -463,38 +463,58 @@ static const uint32_t LQ_C[4] = {0x4b800000u, 0x4b317afdu, 0x4a780626u, 0x496151
 static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
-/* LQ32 steps 1-4.  No subtraction of the maximum, no float->int conversion:
- * integers are read out of float mantissas.
- *   m    = max_i x_i  (NaN dropped)
- *   nref = bits(fma(m, log2e, MAGIC))   MAGIC = 1.5 * 2^23; t = fma(x, log2e, MAGIC) is monotone in x, so this is
- *                                  max_i bits(t_i); for |x*log2e| < 2^22 the low mantissa bits of t hold rne(x*log2e).
- *                                  The row is DEGENERATE (all q = 0, uniform table) when nref is outside
- *                                  [LQ_REF_LO, LQ_REF_HI): +inf, |m*log2e| >= 2^22 - 64, or nothing finite.
- *   t_i  = fma(x_i, log2e, MAGIC),  sh_i = nref - bits(t_i)   (unsigned; = n_max - n_i; >= 32 for -inf; NaN -> q = 0)
- *   f_i  = fma(x_i, log2e, MAGIC - t_i)     residual in [-0.5, 0.5], single rounding
- *   z_i  = fma(fma(fma(c3, f, c2), f, c1), f, MAGICZ)   = 1.5*2^25 + 2^24 (2^f - 1); mantissa = rne(2^22 2^f)
- *   q_i  = sh_i >= 32 ? 0 : (bits(z_i) << 7) >> sh_i    (bits(z) << 7 = mantissa << 7 in [2^28.5, 2^29.5): the
- *                                  exponent field of [2^25, 2^26) ends in 00, so four q fit a uint32 sum)
+/* LQ32, block form: the row is cut into NW = 32 * parts(V) segments of at most 1024
+ * elements, every segment is quantised against ITS OWN reference exponent, and the segment totals are aligned to
+ * the row-wide reference afterwards (block floating point).  Nothing needs the row maximum before the element
+ * pass.  No subtraction of a maximum, no float->int conversion: integers are read out of float mantissas.
+ *
+ *   parts = ceil(V / 32768),  NW = 32 * parts,  G = ceil(V / 4)
+ *   segment w = elements [4 * floor(w * G / NW), min(V, 4 * floor((w + 1) * G / NW)))       (a function of V only)
+ * per segment w:
+ *   m_w   = max x_i  (NaN dropped; -inf when nothing is left)
+ *   n_w   = bits(fma(m_w, log2e, MAGIC))   MAGIC = 1.5 * 2^23; t = fma(x, log2e, MAGIC) is monotone in x, so this is
+ *                                   max bits(t_i); for |x*log2e| < 2^22 the low mantissa bits of t hold rne(x*log2e).
+ *   r_w   = 0 (EMPTY)            if n_w <  LQ_REF_LO    (nothing finite, or m_w * log2e <= -(2^22 - 64))
+ *           0xFFFFFF (POISON)    if n_w >= LQ_REF_HI    (+inf, or m_w * log2e >= 2^22)
+ *           n_w - LQ_REF_LO + 1  otherwise              (24-bit reference code)
+ *   t_i   = fma(x_i, log2e, MAGIC),  sh_i = n_w - bits(t_i)   (unsigned; >= 32 for -inf; NaN -> q = 0)
+ *   f_i   = fma(x_i, log2e, MAGIC - t_i)     residual in [-0.5, 0.5], single rounding
+ *   z_i   = fma(fma(fma(c3, f, c2), f, c1), f, MAGICZ)   = 1.5*2^25 + 2^24 (2^f - 1); mantissa = rne(2^22 2^f)
+ *   q_i   = sh_i >= 32 ? 0 : (bits(z_i) << 7) >> sh_i    (bits(z) << 7 = mantissa << 7 in [2^28.5, 2^29.5): the
+ *                                   exponent field of [2^25, 2^26) ends in 00, so four q fit a uint32 sum)
+ *   S_w   = sum q_i  (< 2^39.5; 0 for EMPTY / POISON segments),  c_i = sum of q_j over j < i inside the segment
+ * per row:
+ *   r     = max_w r_w ;  the row is DEGENERATE (every W_w = 0, uniform table) when r is 0 or POISON
+ *   d_w   = r - r_w ,  W_w = (r_w == 0 || d_w >= 40) ? 0 : S_w >> d_w ,  Q = sum W_w
+ *   C_i   = sum_{w' < w} W_w' + (c_i >> d_w)        (0 instead of the shifted term when W_w is forced to 0)
+ *   cum_i = ((C_i * R) >> s) + i  with (R, s) from Q as below,  cum_V = 2^32
  */
 #define LQ_REF_LO 0x4B000040
 #define LQ_REF_HI 0x4B800000
-#define LQ_DEGENERATE INT32_MIN
+#define LQ_POISON 0xFFFFFFu
 static inline float lq_max(float a, float b) { /* PTX max.f32 / fmaxf: a NaN operand is dropped */
     if (a != a) return b;
     if (b != b) return a;
     return a > b ? a : b;
 }
-static inline int32_t lq_rowref(const float *x, int V) {
-    float m = u2f(0xFF800000u); /* -inf */
-    for (int i = 0; i < V; i++) m = lq_max(m, x[i]);
-    int32_t nref = (int32_t)f2u(fmaf(m, u2f(LQ_LOG2E), u2f(LQ_MAGIC)));
-    if (nref < LQ_REF_LO || nref >= LQ_REF_HI) return LQ_DEGENERATE;
-    return nref;
+static inline int lq_parts(int V) { return (V + 32767) / 32768; }
+static inline int lq_seg_begin(int w, int V) { /* first ELEMENT of segment w (w = NW: V rounded up to 4) */
+    int64_t G = (V + 3) / 4;
+    return (int)(4 * ((w * G) / (32 * lq_parts(V))));
 }
-static inline uint32_t lq_q(float x, int32_t nref) {
-    if (nref == LQ_DEGENERATE || x != x) return 0u;
+static inline uint32_t lq_segcode(const float *x, int e0, int e1) {
+    float m = u2f(0xFF800000u); /* -inf */
+    for (int i = e0; i < e1; i++) m = lq_max(m, x[i]);
+    int32_t n = (int32_t)f2u(fmaf(m, u2f(LQ_LOG2E), u2f(LQ_MAGIC)));
+    if (n < LQ_REF_LO) return 0u;
+    if (n >= LQ_REF_HI) return LQ_POISON;
+    return (uint32_t)(n - LQ_REF_LO + 1);
+}
+static inline uint32_t lq_q(float x, uint32_t code) { /* q of one element against its segment's reference code */
+    if (code == 0u || code == LQ_POISON || x != x) return 0u;
+    uint32_t nref = code - 1u + (uint32_t)LQ_REF_LO;
     float t = fmaf(x, u2f(LQ_LOG2E), u2f(LQ_MAGIC));
-    uint32_t sh = (uint32_t)nref - f2u(t);
+    uint32_t sh = nref - f2u(t);
     if (sh >= 32) return 0u;
     float rn = u2f(LQ_MAGIC) - t;
     float f = fmaf(x, u2f(LQ_LOG2E), rn);
@@ -521,43 +541,82 @@ static inline lq_scale lq_make_scale(uint64_t Q, int V) {
 static inline uint32_t lq_cum(uint64_t C, uint32_t i, lq_scale k) {
     return (uint32_t)(((u128)C * k.R) >> k.s) + i;
 }
+/* Row-level pieces: codes[w], weights W[w] (aligned to the row reference), shifts d[w] (64 = forced to zero). */
+#define LQ_MAX_NW 1024
+typedef struct { int nw; uint32_t code[LQ_MAX_NW]; uint64_t W[LQ_MAX_NW]; int d[LQ_MAX_NW]; uint64_t Q; } lq_row;
+static void lq_row_summary(const float *x, int V, lq_row *r) {
+    r->nw = 32 * lq_parts(V);
+    uint32_t rmax = 0;
+    for (int w = 0; w < r->nw; w++) {
+        int e0 = lq_seg_begin(w, V), e1 = lq_seg_begin(w + 1, V);
+        if (e1 > V) e1 = V;
+        r->code[w] = e0 < e1 ? lq_segcode(x, e0, e1) : 0u;
+        if (r->code[w] > rmax) rmax = r->code[w];
+    }
+    r->Q = 0;
+    for (int w = 0; w < r->nw; w++) {
+        int e0 = lq_seg_begin(w, V), e1 = lq_seg_begin(w + 1, V);
+        if (e1 > V) e1 = V;
+        uint64_t S = 0;
+        for (int i = e0; i < e1; i++) S += lq_q(x[i], r->code[w]);
+        uint32_t dw = rmax - r->code[w];
+        int dead = (rmax == 0u || rmax == LQ_POISON || r->code[w] == 0u || dw >= 40u);
+        r->d[w] = dead ? 64 : (int)dw;
+        r->W[w] = dead ? 0 : (S >> dw);
+        r->Q += r->W[w];
+    }
+}
 /* Exclusive cumulative table, V entries (cum[0] = 0); the total 2^32 is implicit. */
 int orc_lq32_cdf(const float *logits, int64_t rows, int V, int64_t row_stride, uint32_t *cum) {
-    if (V < 1 || V > (1 << 20)) return ORC_E_ARG;
+    if (V < 1 || V > 32768 * (LQ_MAX_NW / 32)) return ORC_E_ARG;
+    lq_row *R = (lq_row *)malloc(sizeof(lq_row));
+    if (!R) return ORC_E_ARG;
     for (int64_t r = 0; r < rows; r++) {
         const float *x = logits + r * row_stride;
-        int32_t m = lq_rowref(x, V);
-        uint64_t Q = 0;
-        for (int i = 0; i < V; i++) Q += lq_q(x[i], m);
-        lq_scale k = lq_make_scale(Q, V);
-        uint64_t C = 0;
-        for (int i = 0; i < V; i++) {
-            cum[r * V + i] = lq_cum(C, (uint32_t)i, k);
-            C += lq_q(x[i], m);
+        lq_row_summary(x, V, R);
+        lq_scale k = lq_make_scale(R->Q, V);
+        uint64_t front = 0;
+        for (int w = 0; w < R->nw; w++) {
+            int e0 = lq_seg_begin(w, V), e1 = lq_seg_begin(w + 1, V);
+            if (e1 > V) e1 = V;
+            uint64_t c = 0;
+            for (int i = e0; i < e1; i++) {
+                uint64_t C = front + (R->d[w] >= 64 ? 0 : (c >> R->d[w]));
+                cum[r * V + i] = lq_cum(C, (uint32_t)i, k);
+                c += lq_q(x[i], R->code[w]);
+            }
+            front += R->W[w];
         }
     }
+    free(R);
     return ORC_OK;
 }
 /* (cum[sym], cum[sym+1]) per row without materialising the table; hi of the last symbol is 2^32. */
 int orc_lq32_lookup(const float *logits, int64_t rows, int V, int64_t row_stride,
                     const int32_t *syms, uint32_t *lo, uint64_t *hi) {
+    if (V < 1 || V > 32768 * (LQ_MAX_NW / 32)) return ORC_E_ARG;
+    lq_row *R = (lq_row *)malloc(sizeof(lq_row));
+    if (!R) return ORC_E_ARG;
+    int rc = ORC_OK;
     for (int64_t r = 0; r < rows; r++) {
         const float *x = logits + r * row_stride;
         int32_t s = syms[r];
-        if (s < 0 || s >= V) return ORC_E_SYMBOL;
-        int32_t m = lq_rowref(x, V);
-        uint64_t Q = 0, C = 0, qs = 0;
-        for (int i = 0; i < V; i++) {
-            uint32_t q = lq_q(x[i], m);
-            if (i < s) C += q;
-            if (i == s) qs = q;
-            Q += q;
-        }
-        lq_scale k = lq_make_scale(Q, V);
-        lo[r] = lq_cum(C, (uint32_t)s, k);
-        hi[r] = (s == V - 1) ? ((uint64_t)1 << 32) : (uint64_t)lq_cum(C + qs, (uint32_t)s + 1, k);
+        if (s < 0 || s >= V) { rc = ORC_E_SYMBOL; break; }
+        lq_row_summary(x, V, R);
+        lq_scale k = lq_make_scale(R->Q, V);
+        uint64_t front = 0;
+        int w = 0;
+        while (lq_seg_begin(w + 1, V) <= s) front += R->W[w++];
+        uint64_t c = 0;
+        for (int i = lq_seg_begin(w, V); i < s; i++) c += lq_q(x[i], R->code[w]);
+        uint64_t qs = lq_q(x[s], R->code[w]);
+        int d = R->d[w];
+        lo[r] = lq_cum(front + (d >= 64 ? 0 : (c >> d)), (uint32_t)s, k);
+        hi[r] = (s == V - 1) ? ((uint64_t)1 << 32)
+                             : (uint64_t)lq_cum(front + (d >= 64 ? 0 : ((c + qs) >> d)), (uint32_t)s + 1, k);
     }
-    return ORC_OK;
+    free(R);
+    return rc;
 }
 
 /*

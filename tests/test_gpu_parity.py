@@ -62,9 +62,10 @@ def test_cdf_build_bit_exact(V):
     assert (np.diff(full, axis=1) >= 1).all()
 
 
-@pytest.mark.parametrize("V", [32772, 50000, 65536, 65540, 128256, 131072, 151936, 262144])
-def test_cluster_rows_bit_exact(V):
-    """Vocabularies wider than one CTA (32768): the row is split over a 2 / 4 / 8-CTA cluster."""
+@pytest.mark.parametrize("V", [32772, 50000, 65536, 65540, 70001, 100000, 128256, 131072, 151936, 200003, 262144])
+def test_multi_part_rows_bit_exact(V):
+    """Vocabularies wider than one tile (32768): the row is ceil(V / 32768) tiles (2 .. 8 parts, any count);
+    odd vocabularies take the scalar-load path with the same segmentation."""
     rng = np.random.default_rng(V)
     logits = _special_rows(V, rng)[:9]
     logits = np.concatenate([logits, (rng.standard_normal((5, V)) * 6).astype(np.float32)])
@@ -78,8 +79,8 @@ def test_cluster_rows_bit_exact(V):
     assert np.array_equal(pairs[:, 1].astype(np.uint64), hi & 0xFFFFFFFF)
 
 
-@pytest.mark.parametrize("V,S,T", [(128256, 6, 12), (65536, 40, 5), (262144, 3, 7)])
-def test_cluster_encode_decode_roundtrip(V, S, T):
+@pytest.mark.parametrize("V,S,T", [(128256, 6, 12), (65536, 40, 5), (262144, 3, 7), (151936, 5, 9), (70001, 4, 6)])
+def test_multi_part_encode_decode_roundtrip(V, S, T):
     rng = np.random.default_rng(V + S)
     logits = (rng.standard_normal((S, T, V)) * 5).astype(np.float32)
     syms = rng.integers(0, V, (S, T)).astype(np.int32)
@@ -113,9 +114,80 @@ def test_streams_ending_inside_the_first_bit_window(V, S):
         assert np.array_equal(coder.StreamDecoder(streams).decode_logits(dl).cpu().numpy(), syms)
 
 
-def test_wide_unaligned_vocab_is_rejected():
+def test_vocab_out_of_range_is_rejected():
     with pytest.raises(_ffi.LacError):
-        coder.cdf_build(torch.zeros((2, 40001), dtype=torch.float32, device="cuda"))
+        coder.cdf_build(torch.zeros((1, 262145), dtype=torch.float32, device="cuda"))
+
+
+def test_caller_workspace_gives_the_same_result_and_small_workspaces_chunk():
+    rng = np.random.default_rng(77)
+    S, T, V = 9, 7, 4096
+    logits = (rng.standard_normal((S, T, V)) * 4).astype(np.float32)
+    syms = rng.integers(0, V, (S, T)).astype(np.int32)
+    dl, ds = _dev(logits), _dev(syms)
+    ref = coder.StreamEncoder(S)
+    ref.encode_logits(dl, ds, finish=True)
+    want, _ = ref.bitstreams()
+    for rows in (S * T, 5, 1):  # full, a few rows, one row of scratch: the calls work through the rows in launches
+        ws = coder.Workspace(rows, V)
+        enc = coder.StreamEncoder(S)
+        enc.encode_logits(dl, ds, finish=True, ws=ws)
+        got, _ = enc.bitstreams()
+        assert got == want
+        assert np.array_equal(coder.StreamDecoder(got).decode_logits(dl, ws=ws).cpu().numpy(), syms)
+        pairs = coder.cdf_lookup(dl.view(S * T, V), ds.view(-1), ws=ws).cpu().numpy()
+        assert np.array_equal(pairs, coder.cdf_lookup(dl.view(S * T, V), ds.view(-1)).cpu().numpy())
+        assert np.array_equal(coder.cdf_build(dl.view(S * T, V), ws=ws).cpu().numpy(),
+                              coder.cdf_build(dl.view(S * T, V)).cpu().numpy())
+
+
+def test_fused_encoder_equals_lookup_plus_pairs_coder():
+    """lac_ac_encode_logits_f32 (one fused kernel) against lac_cdf_lookup_f32 + lac_ac_encode_pairs, all slice
+    shapes the launcher distinguishes (T = 1, 2, 5, 16, 40), ragged streams, state carried across calls."""
+    rng = np.random.default_rng(78)
+    S, V = 37, 1000
+    for T in (1, 2, 5, 16, 40):
+        logits = (rng.standard_normal((S, T, V)) * 5).astype(np.float32)
+        syms = rng.integers(0, V, (S, T)).astype(np.int32)
+        ntok = rng.integers(0, T + 1, S).astype(np.int32)
+        dl, ds, dn = _dev(logits), _dev(syms), _dev(ntok)
+        a, b = coder.StreamEncoder(S), coder.StreamEncoder(S)
+        for rep in range(3):  # three calls on the same streams, the last one finishes
+            a.encode_logits(dl, ds, ntok=dn, finish=(rep == 2))
+            pairs = coder.cdf_lookup(dl.view(S * T, V), ds.view(-1))
+            b.encode_pairs(pairs.view(S, T, 2), ntok=dn, finish=(rep == 2))
+        sa, na = a.bitstreams()
+        sb, nb = b.bitstreams()
+        assert sa == sb and np.array_equal(na, nb)
+
+
+def test_truncated_stream_is_reported():
+    """The reference raises 'predictor range does not correspond to val' (arith_code.py:277-278) on a stream that
+    does not belong to the model; here the decoder flags streams from which it consumed more bits than they hold."""
+    rng = np.random.default_rng(79)
+    S, T, V = 8, 64, 512
+    logits = (rng.standard_normal((S, T, V)) * 2).astype(np.float32)
+    syms = rng.integers(0, V, (S, T)).astype(np.int32)
+    dl = _dev(logits)
+    enc = coder.StreamEncoder(S)
+    enc.encode_logits(dl, _dev(syms), finish=True)
+    streams, _ = enc.bitstreams()
+    assert np.array_equal(coder.StreamDecoder(streams).decode_logits(dl).cpu().numpy(), syms)
+    cut = [b[: len(b) // 3] if i % 2 else b for i, b in enumerate(streams)]
+    dec = coder.StreamDecoder(cut)
+    with pytest.raises(_ffi.LacError) as e:
+        dec.decode_logits(dl)
+    assert e.value.code == _ffi.LAC_E_STREAM
+    st = dec.state.cpu().numpy().view(np.uint32).reshape(S, 10)[:, 8]
+    assert all(bool(st[i] & _ffi.LAC_ST_TRUNC) == bool(i % 2) for i in range(S))
+    data = np.frombuffer(b"".join(cut), dtype=np.uint8)
+    offs = np.concatenate([[0], np.cumsum([len(b) for b in cut])]).astype(np.int64)
+    with pytest.raises(_ffi.LacError) as e:
+        coder.decode_logits_host(logits, data, offs)
+    assert e.value.code == _ffi.LAC_E_STREAM
+    with pytest.raises(_ffi.LacError) as e:
+        coder.decode_logits_host(logits, data, offs[::-1].copy())
+    assert e.value.code == _ffi.LAC_E_ARG
 
 
 def test_cdf_build_unaligned_rows_use_scalar_path():
@@ -249,6 +321,60 @@ def test_capacity_overflow_is_reported():
     with pytest.raises(_ffi.LacError) as e:
         enc.bitstreams()
     assert e.value.code == _ffi.LAC_E_CAP
+
+
+def test_capacity_overflow_never_writes_outside_the_stream_region():
+    """Once a stream overflows its out_stride bytes nothing may be written any more: not past the buffer, not into
+    the neighbouring stream (carry ripples used to do both)."""
+    rng = np.random.default_rng(41)
+    S, T, V, cap = 33, 96, 256, 8
+    logits = _dev((rng.standard_normal((S, T, V)) * 4).astype(np.float32))
+    syms_h = rng.integers(0, V, (S, T)).astype(np.int32)
+    ntok_h = np.full(S, T, dtype=np.int32)
+    ntok_h[::2] = 3  # every other stream is short enough to fit: its bytes must survive its neighbours' overflow
+    syms, ntok = _dev(syms_h), _dev(ntok_h)
+    pairs = coder.cdf_lookup(logits.view(S * T, V), syms.view(-1))
+    # canaries: [S, cap] stream regions inside a larger buffer filled with 0xA5
+    buf = torch.full((S + 4, cap), 0xA5, dtype=torch.uint8, device="cuda")
+    state = torch.zeros((S, _ffi.ENC_STATE_BYTES), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    L = _ffi.lib()
+    _ffi.check(L.lac_enc_init(state.data_ptr(), S, 48, st))
+    for lo in range(0, T, 32):  # several calls: an overflowed stream is re-opened, too
+        n = torch.clamp(ntok - lo, 0, 32).to(torch.int32)
+        _ffi.check(L.lac_ac_encode_pairs(pairs.view(S, T, 2)[:, lo:].data_ptr(), S, 32, T, 1, n.data_ptr(),
+                                         state.data_ptr(), buf[2:].data_ptr(), cap, int(lo + 32 >= T), 48, st))
+    torch.cuda.synchronize()
+    host = buf.cpu().numpy()
+    assert (host[:2] == 0xA5).all() and (host[S + 2:] == 0xA5).all(), "wrote outside the output buffer"
+    status = state.cpu().numpy().view(np.uint32).reshape(S, 8)[:, 6]
+    for s in range(S):
+        if ntok_h[s] == 3:
+            assert status[s] == 0
+            lo_, hi_ = orc.lq32_lookup(logits[s, :3].cpu().numpy(), syms_h[s, :3])
+            want = orc.pack_bits(orc.ac_encode_pairs(lo_, hi_, prec=48)).tobytes()
+            assert host[2 + s, : len(want)].tobytes() == want, f"stream {s} corrupted by a neighbour's overflow"
+        else:
+            assert status[s] & _ffi.LAC_ST_CAP
+
+
+def test_bad_symbol_reaches_the_stream_status():
+    """A symbol outside [0, V) must not be coded as nothing: the reference raises 'unknown symbol'
+    (arith_code.py:104-105)."""
+    rng = np.random.default_rng(42)
+    S, T, V = 3, 5, 100
+    logits = _dev(rng.standard_normal((S, T, V)).astype(np.float32))
+    syms_h = rng.integers(0, V, (S, T)).astype(np.int32)
+    syms_h[1, 2] = V
+    enc = coder.StreamEncoder(S)
+    enc.encode_logits(logits, _dev(syms_h), finish=True)
+    with pytest.raises(_ffi.LacError) as e:
+        enc.bitstreams()
+    assert e.value.code == _ffi.LAC_E_SYMBOL
+    flat = rng.standard_normal((S, T, V)).astype(np.float32)
+    with pytest.raises(_ffi.LacError) as e:
+        coder.encode_logits_host(flat, syms_h)
+    assert e.value.code == _ffi.LAC_E_SYMBOL
 
 
 # ------------------------------------------------------------------ golden vectors of the real reference
@@ -558,18 +684,23 @@ def test_special_rows_through_both_second_passes(V):
 
 
 @pytest.mark.gpu
-def test_lookup_and_decode_are_cuda_graph_capturable():
-    """The device entry points are asynchronous and use only stream-ordered work (cudaMallocAsync scratch
-    included), so a model-in-the-loop step can be captured into a CUDA graph and replayed."""
+@pytest.mark.parametrize("with_ws", [True, False])
+def test_encode_and_decode_steps_are_cuda_graph_capturable(with_ws):
+    """The device entry points are asynchronous and use only stream-ordered work (with a caller workspace: no
+    allocation at all; without: cudaMallocAsync scratch), so a model-in-the-loop step can be captured into a CUDA
+    graph and replayed: several replays walk the coder state token by token."""
     rng = np.random.default_rng(9)
-    S, V = 64, 32000
-    logits = _dev((rng.standard_normal((S, 1, V)) * 4).astype(np.float32))
-    syms = _dev(rng.integers(0, V, (S, 1)).astype(np.int32))
+    S, V, T = 64, 32000, 5
+    logits_all = _dev((rng.standard_normal((S, T, V)) * 4).astype(np.float32))
+    syms_all = _dev(rng.integers(0, V, (S, T)).astype(np.int32))
     ref_enc = coder.StreamEncoder(S, capacity_bytes=256)
-    ref_enc.encode_logits(logits, syms, finish=True)           # also warms the scratch pool up
+    ref_enc.encode_logits(logits_all, syms_all, finish=True)           # also warms the scratch pool up
     want, _ = ref_enc.bitstreams()
+    ws = coder.Workspace(S, V) if with_ws else None
+    wsp = (ws.ptr, ws.nbytes) if ws else (None, 0)
+    logits = torch.empty((S, 1, V), dtype=torch.float32, device="cuda")   # static graph inputs
+    syms = torch.empty((S, 1), dtype=torch.int32, device="cuda")
     enc = coder.StreamEncoder(S, capacity_bytes=256)
-    pairs = torch.empty((S, 2), dtype=torch.int32, device="cuda")
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     graph = torch.cuda.CUDAGraph()
@@ -577,11 +708,15 @@ def test_lookup_and_decode_are_cuda_graph_capturable():
     with torch.cuda.stream(side):
         with torch.cuda.graph(graph, stream=side):
             st = torch.cuda.current_stream().cuda_stream
-            _ffi.check(L.lac_cdf_lookup_f32(logits.data_ptr(), S, V, V, syms.data_ptr(), pairs.data_ptr(), None, st))
-            _ffi.check(L.lac_ac_encode_pairs(pairs.data_ptr(), S, 1, 1, 1, None, enc.state.data_ptr(),
-                                             enc.out.data_ptr(), enc.cap, 1, enc.prec, st))
+            _ffi.check(L.lac_ac_encode_logits_f32(logits.data_ptr(), S, 1, V, V, V, syms.data_ptr(), 1, None,
+                                                  enc.state.data_ptr(), enc.out.data_ptr(), enc.cap, 0, enc.prec,
+                                                  *wsp, st))
     torch.cuda.current_stream().wait_stream(side)
-    graph.replay()
+    for t in range(T):
+        logits.copy_(logits_all[:, t:t + 1])
+        syms.copy_(syms_all[:, t:t + 1])
+        graph.replay()
+    enc.finish()
     torch.cuda.synchronize()
     got, _ = enc.bitstreams()
     assert got == want
@@ -595,8 +730,10 @@ def test_lookup_and_decode_are_cuda_graph_capturable():
             st = torch.cuda.current_stream().cuda_stream
             _ffi.check(L.lac_ac_decode_logits_f32(logits.data_ptr(), S, 1, V, V, V, None, dec.state.data_ptr(),
                                                   dec.bytes.data_ptr(), dec.offsets.data_ptr(), out.data_ptr(), 1,
-                                                  dec.prec, st))
+                                                  dec.prec, *wsp, st))
     torch.cuda.current_stream().wait_stream(side)
-    g2.replay()
-    torch.cuda.synchronize()
-    assert torch.equal(out, syms)
+    for t in range(T):
+        logits.copy_(logits_all[:, t:t + 1])
+        g2.replay()
+        assert torch.equal(out, syms_all[:, t:t + 1])
+    assert dec.status() == 0
