@@ -204,8 +204,9 @@ class Job:
         self.ws_bytes = int(L.lac_workspace_bytes(self.rows, V))     # caller-provided scratch: no allocation per call
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
         self.stream = torch.cuda.current_stream().cuda_stream
-        # kernels per job: enc_init + n x (summary, encode_fused) + dec_init + n x (summary, decode_serial)
-        self.launches = 2 + 4 * self.n_slices
+        # kernels per job: enc_init + n x (summary, pair, encode_pairs) + dec_init + n x (summary, decode_serial)
+        # (slices of <= 4 tokens: summary + one fused encoder kernel)
+        self.launches = 2 + (5 if T > 4 else 4) * self.n_slices
 
     def encode(self, ev=None):
         L, ck, S, T, V, st = self.L, self.ffi.check, self.S, self.T, self.V, self.stream
@@ -213,7 +214,7 @@ class Job:
         for k in range(self.n_slices):
             if ev is not None: ev[k][0].record()
             # summary pass (fused softmax -> quantise -> clamp -> segment sums, one HBM pass over the logits), then
-            # ONE kernel: (lo, hi) of the coded symbols + range coder, bytes staged in shared memory
+            # (lo, hi) of the coded symbols (one warp per row) and the range coder (one thread per stream)
             ck(L.lac_ac_encode_logits_f32(self.logits.data_ptr(), S, T, T * V, V, V, self.syms[k].data_ptr(), T, None,
                                           self.enc_state.data_ptr(), self.out.data_ptr(), self.cap,
                                           int(k == self.n_slices - 1), PREC, self.ws.data_ptr(), self.ws_bytes, st))
@@ -331,11 +332,12 @@ def run_gpu(args):
         clocks2 = Clocks(local)
         clocks2.start()
         time.sleep(0.3)
-        evs2 = [job2.events() for _ in range(args.v128_jobs)]
+        evs2 = [job2.events() for _ in range(min(4, args.v128_jobs))]
         b2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         b2.record()
-        for ev in evs2:
+        for j in range(args.v128_jobs):
+            ev = evs2[j] if j < len(evs2) else None
             job2.encode(ev); job2.decode(ev)
         e2.record()
         torch.cuda.synchronize()
@@ -405,8 +407,8 @@ def run_gpu(args):
             "roofline": {"bound": "hbm",
                          "kernel": "summary_kernel (fused softmax -> fixed-total quantisation -> min-frequency clamp -> "
                                    "segment prefix sums; the one HBM pass over the logits), timed through the whole "
-                                   "lac_ac_encode_logits_f32 call, i.e. together with encode_fused_kernel (symbol ranges + "
-                                   "range coder); the ncu launch list under profiles/ gives the split",
+                                   "lac_ac_encode_logits_f32 call, i.e. together with pair_kernel (symbol ranges) and "
+                                   "encode_pairs_kernel (range coder); the ncu launch list under profiles/ gives the split",
                          "achieved": enc_gbs, "peak": peak, "unit": "GB/s", "frac": enc_gbs / peak,
                          "traffic": measured_traffic("summary_kernel", V, rows), "peak_source": peak_src,
                          "peak_note": "the peak is the copy-measured (read + write) figure; a read-only stream reaches 7.2-7.8 TB/s on this part (profiles/microbench/tma_stream_b200.txt), so frac may exceed 1",
@@ -444,7 +446,7 @@ def main():
     ap.add_argument("--chunk-tokens", type=int, default=CHUNK_TOKENS)
     ap.add_argument("--no-v128", action="store_true")
     ap.add_argument("--v128-tokens", type=int, default=256)
-    ap.add_argument("--v128-jobs", type=int, default=4)
+    ap.add_argument("--v128-jobs", type=int, default=100)
     args = ap.parse_args()
     globals().update(VOCAB=args.vocab, STREAMS=args.streams, SLICE=args.slice, CHUNK_TOKENS=args.chunk_tokens)
     if args.impl == "reference":

@@ -121,8 +121,18 @@ class StreamEncoder:
         self.device = torch.device(device)
         self.state = torch.zeros((self.n, _ffi.ENC_STATE_BYTES), dtype=torch.uint8, device=self.device)
         self.out = torch.zeros((self.n, self.cap), dtype=torch.uint8, device=self.device)
+        self.reset()
+
+    def reset(self):
+        """Start n_streams new streams in the same device buffers (their addresses stay valid for CUDA graphs)."""
         check(lib().lac_enc_init(self.state.data_ptr(), self.n, self.prec, _cur_stream()))
         self.finished = False
+
+    def status(self) -> int:
+        """OR of the streams' status words (one 4-byte read)."""
+        flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        check(lib().lac_enc_status(self.state.data_ptr(), self.n, flag.data_ptr(), _cur_stream()))
+        return int(flag.item()) & 0xFFFFFFFF
 
     def _ntok(self, ntok):
         if ntok is None:
@@ -249,11 +259,29 @@ class StreamDecoder:
     """n_streams independent A_from_bin decoders (arith_code.py:248-334) on the GPU, decoding a
     known number of tokens (the reference has no length framing; the container supplies it)."""
 
-    def __init__(self, streams: Sequence[bytes], prec: int = DEFAULT_PREC, device="cuda"):
+    def __init__(self, streams: Sequence[bytes], prec: int = DEFAULT_PREC, device="cuda",
+                 capacity_bytes: Optional[int] = None):
         self.n, self.prec = len(streams), int(prec)
         self.device = torch.device(device)
-        self.bytes, self.offsets = pack_streams(streams, self.device)
+        total = sum(len(s) for s in streams) + 16
+        self.bytes = torch.zeros(max(total, int(capacity_bytes or 0)), dtype=torch.uint8, device=self.device)
+        self.offsets = torch.zeros(self.n + 1, dtype=torch.int64, device=self.device)
         self.state = torch.zeros((self.n, _ffi.DEC_STATE_BYTES), dtype=torch.uint8, device=self.device)
+        self.reset(streams)
+
+    def reset(self, streams: Sequence[bytes]):
+        """Start decoding a new set of n_streams streams in the same device buffers (addresses stay valid for CUDA
+        graphs); they must fit the byte capacity given at construction."""
+        if len(streams) != self.n:
+            raise LacError(_ffi.LAC_E_ARG, f"expected {self.n} streams, got {len(streams)}")
+        offs = np.zeros(self.n + 1, dtype=np.int64)
+        np.cumsum([len(s) for s in streams], out=offs[1:])
+        if int(offs[-1]) + 16 > self.bytes.numel():
+            raise LacError(_ffi.LAC_E_CAP, f"{int(offs[-1])} stream bytes exceed the decoder's capacity "
+                                           f"({self.bytes.numel() - 16}); construct it with capacity_bytes=")
+        buf = np.frombuffer(b"".join(streams) + b"\0" * 16, dtype=np.uint8)
+        self.bytes[: len(buf)].copy_(torch.from_numpy(buf.copy()))
+        self.offsets.copy_(torch.from_numpy(offs))
         check(lib().lac_dec_init(self.state.data_ptr(), self.n, self.prec, self.bytes.data_ptr(),
                                  self.offsets.data_ptr(), _cur_stream()))
 

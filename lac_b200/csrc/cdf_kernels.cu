@@ -225,15 +225,17 @@ summary_kernel(const __grid_constant__ SumParams sp, uint64_t* __restrict__ summ
 
 // ------------------------------------------------------------------ LOOKUP (second pass of lac_cdf_lookup_f32)
 // One warp per row, all rows independent (rowsum.cuh).  ~2 % extra HBM traffic.
+// Row r = (s, t) = (r / T, r % T): logits at base + s * so + t * st, symbol at syms[s * sym_stride + t].
 template <int VEC, int CL>
 __global__ void __launch_bounds__(256)
-pair_kernel(const float* __restrict__ logits, int64_t rows, int64_t row_stride, int V,
-            const uint64_t* __restrict__ summ, const int32_t* __restrict__ syms, uint32_t* __restrict__ pairs,
-            uint32_t* __restrict__ status) {
+pair_kernel(const float* __restrict__ logits, int64_t rows, int64_t T, int64_t so, int64_t st, int V,
+            const uint64_t* __restrict__ summ, const int32_t* __restrict__ syms, int64_t sym_stride,
+            uint32_t* __restrict__ pairs, uint32_t* __restrict__ status) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= rows) return;
-    const int sym = __ldg(syms + r);
+    const int64_t s = r / T, t = r - s * T;
+    const int sym = __ldg(syms + s * sym_stride + t);
     if (sym < 0 || sym >= V) {
         if (lane == 0) {
             // sentinel the coder turns into LAC_ST_SYMBOL on the stream (the reference raises "unknown symbol",
@@ -243,7 +245,7 @@ pair_kernel(const float* __restrict__ logits, int64_t rows, int64_t row_stride, 
         }
         return;
     }
-    const uint2 o = warp_symbol_range<VEC, CL>(logits + r * row_stride, V, summ + r * (32 * CL), sym, lane);
+    const uint2 o = warp_symbol_range<VEC, CL>(logits + s * so + t * st, V, summ + r * (32 * CL), sym, lane);
     if (lane == 0) *reinterpret_cast<uint2*>(pairs + 2 * r) = o;
 }
 
@@ -364,12 +366,13 @@ cudaError_t launch_summary(const float* base, int64_t n_outer, int64_t T, int64_
 // chunks) and the tile index (the mul-shift division by `parts` is exact below 2^28 tiles).
 int64_t summ_chunk_rows(int parts) {
     static const int64_t budget = getenv("LAC_SUMMARY_BYTES") ? atoll(getenv("LAC_SUMMARY_BYTES")) : (64ll << 20);
-    int64_t rows = budget / (32 * parts * 8);
+    int64_t rows = budget / (32 * parts * 8 + 8);
     const int64_t lim = ((1ll << 28) - 1) / parts;
     if (rows > lim) rows = lim;
     return rows < 1 ? 1 : rows;
 }
-size_t summ_bytes(int64_t rows, int parts) { return (size_t)rows * 32 * (size_t)parts * 8; }
+size_t summ_only_bytes(int64_t rows, int parts) { return (size_t)rows * 32 * (size_t)parts * 8; }
+size_t summ_bytes(int64_t rows, int parts) { return summ_only_bytes(rows, parts) + (size_t)rows * 8; }
 // rows of summary that fit the scratch the call will use: the caller's workspace if it holds at least one row
 int64_t summ_rows_for(int64_t want, int parts, const void* ws, size_t ws_bytes) {
     int64_t chunk = summ_chunk_rows(parts);
@@ -407,6 +410,27 @@ cudaError_t scratch_put(Scratch* sc, cudaStream_t st) {
     return cudaSuccess;
 }
 
+cudaError_t launch_pairs_status(const float* logits, int64_t n, int64_t T, int64_t so, int64_t st_, int V, int parts,
+                                int path, const uint64_t* summ, const int32_t* syms, int64_t sym_stride,
+                                uint32_t* pairs, uint32_t* status, cudaStream_t st) {
+    const int64_t rows = n * T;
+    if (rows == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((rows + 7) / 8);
+#define LAC_PAIR(CL_)                                                                                                 \
+    if (path == 0)                                                                                                    \
+        pair_kernel<1, CL_><<<blocks, 256, 0, st>>>(logits, rows, T, so, st_, V, summ, syms, sym_stride, pairs, status); \
+    else                                                                                                              \
+        pair_kernel<4, CL_><<<blocks, 256, 0, st>>>(logits, rows, T, so, st_, V, summ, syms, sym_stride, pairs, status)
+    LAC_BY_PARTS(parts, LAC_PAIR)
+#undef LAC_PAIR
+    return cudaGetLastError();
+}
+cudaError_t launch_pairs(const float* logits, int64_t n, int64_t T, int64_t so, int64_t st_, int V, int parts, int path,
+                         const uint64_t* summ, const int32_t* syms, int64_t sym_stride, uint32_t* pairs,
+                         cudaStream_t st) {
+    return launch_pairs_status(logits, n, T, so, st_, V, parts, path, summ, syms, sym_stride, pairs, nullptr, st);
+}
+
 // lac_cdf_lookup_f32: summary pass + one warp per row for the pair.
 cudaError_t launch_lookup(const float* logits, int64_t rows, int V, int64_t row_stride, const int32_t* syms,
                           uint32_t* pairs, uint32_t* status, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -424,15 +448,9 @@ cudaError_t launch_lookup(const float* logits, int64_t rows, int V, int64_t row_
         const float* base = logits + r0 * row_stride;
         e = launch_summary(base, rn, 1, row_stride, 0, V, parts, path, 0, summ, st);
         if (e != cudaSuccess) break;
-        const unsigned blocks = (unsigned)((rn + 7) / 8);
-        uint32_t* stat = status ? status + r0 : nullptr;
-#define LAC_PAIR(CL_)                                                                                              \
-    if (path == 0)                                                                                                 \
-        pair_kernel<1, CL_><<<blocks, 256, 0, st>>>(base, rn, row_stride, V, summ, syms + r0, pairs + 2 * r0, stat); \
-    else                                                                                                           \
-        pair_kernel<4, CL_><<<blocks, 256, 0, st>>>(base, rn, row_stride, V, summ, syms + r0, pairs + 2 * r0, stat)
-        LAC_BY_PARTS(parts, LAC_PAIR)
-#undef LAC_PAIR
+        e = launch_pairs_status(base, rn, 1, row_stride, 0, V, parts, path, summ, syms + r0, 1, pairs + 2 * r0,
+                                status ? status + r0 : nullptr, st);
+        if (e != cudaSuccess) break;
         e = cudaGetLastError();
     }
     const cudaError_t ef = scratch_put(&sc, st);

@@ -50,7 +50,7 @@ __device__ __forceinline__ int64_t warp_sum_i64(int64_t v) {
 // ------------------------------------------------------------------ pairs encoder
 __global__ void encode_pairs_kernel(const uint2* __restrict__ pairs, int64_t n_streams, int64_t T,
                                     int64_t stream_stride, int64_t tok_stride, const int32_t* __restrict__ ntok,
-                                    lac_enc_state* __restrict__ state, uint8_t* __restrict__ out,
+                                    int64_t t0, lac_enc_state* __restrict__ state, uint8_t* __restrict__ out,
                                     int64_t out_stride, int finish, int P) {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= n_streams) return;
@@ -58,7 +58,11 @@ __global__ void encode_pairs_kernel(const uint2* __restrict__ pairs, int64_t n_s
     coder::BitWriter bw;
     bw.open(out + s * out_stride, (uint64_t)out_stride, state[s].nbits);
     bw.status = state[s].status;
-    const int64_t Ts = ntok ? (int64_t)ntok[s] : T;
+    int64_t Ts = T;  // ntok counts from t0 tokens before the first pair of this call
+    if (ntok) {
+        Ts = (int64_t)ntok[s] - t0;
+        Ts = Ts < 0 ? 0 : (Ts > T ? T : Ts);
+    }
     const uint2* p = pairs + s * stream_stride;
     // the pairs of a stream are T * 8 bytes apart from the next stream's, so every load is its own memory
     // transaction: fetch them eight tokens at a time (independent loads in flight together), then code serially
@@ -643,6 +647,11 @@ cudaError_t launch_enc_init(lac_enc_state* state, int64_t n, int P, cudaStream_t
 cudaError_t launch_encode_pairs(const uint32_t* pairs, int64_t n, int64_t T, int64_t ss, int64_t ts,
                                 const int32_t* ntok, lac_enc_state* state, uint8_t* out, int64_t out_stride,
                                 int finish, int P, cudaStream_t st) {
+    return launch_encode_pairs_at(pairs, n, T, ss, ts, ntok, 0, state, out, out_stride, finish, P, st);
+}
+cudaError_t launch_encode_pairs_at(const uint32_t* pairs, int64_t n, int64_t T, int64_t ss, int64_t ts,
+                                   const int32_t* ntok, int64_t t0, lac_enc_state* state, uint8_t* out,
+                                   int64_t out_stride, int finish, int P, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     // Each thread is a long dependent chain with data-dependent inner loops (bits per token differ per stream),
     // so few streams per warp (less divergence) on many SMs (more schedulers) beat dense blocks.
@@ -650,11 +659,19 @@ cudaError_t launch_encode_pairs(const uint32_t* pairs, int64_t n, int64_t T, int
     static const int tpb_env = getenv("LAC_CODER_TPB") ? atoi(getenv("LAC_CODER_TPB")) : 2;
     const int tpb = tpb_env < 1 ? 1 : (tpb_env > 1024 ? 1024 : tpb_env);
     encode_pairs_kernel<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, st>>>(reinterpret_cast<const uint2*>(pairs), n, T, ss,
-                                                                  ts, ntok, state, out, out_stride, finish, P);
+                                                                  ts, ntok, t0, state, out, out_stride, finish, P);
     return cudaGetLastError();
 }
 
-// lac_ac_encode_logits_f32: per token chunk (the summary scratch bounds it) summary pass + fused encoder.
+// lac_ac_encode_logits_f32: per token chunk (the scratch bounds it) the summary pass, then
+//   T <= 4 (the model-in-the-loop step): ONE fused kernel (symbol ranges + coder, pairs in shared memory);
+//   longer slices: pair_kernel over all rows at once (thousands of independent warps, ~20 us per 16k rows) into
+//   the scratch, then the thread-per-stream coder.  A fused kernel keeps 8 warps of registers resident per stream
+//   for the whole serial coding chain -- measured 52 us per [1024 x 16] slice against 37 us for the two kernels.
+cudaError_t launch_pairs(const float* logits, int64_t n, int64_t T, int64_t ss, int64_t ts, int V, int parts, int path,
+                         const uint64_t* summ, const int32_t* syms, int64_t sym_stride, uint32_t* pairs,
+                         cudaStream_t st);  // cdf_kernels.cu
+
 cudaError_t launch_encode_logits(const float* logits, int64_t n, int64_t T, int64_t ss, int64_t ts, int V,
                                  const int32_t* syms, int64_t sym_stride, const int32_t* ntok, lac_enc_state* state,
                                  uint8_t* out, int64_t out_stride, int finish, int P, void* ws, size_t ws_bytes,
@@ -666,14 +683,24 @@ cudaError_t launch_encode_logits(const float* logits, int64_t n, int64_t T, int6
     const int64_t Tn = T < 1 ? 1 : T;
     int64_t tc = summ_rows_for(n * Tn, parts, ws, ws_bytes) / n;
     tc = tc < 1 ? 1 : (tc > Tn ? Tn : tc);
+    const bool fused = T <= 4;
     Scratch sc;
     cudaError_t e = scratch_get(&sc, summ_bytes(n * tc, parts), ws, ws_bytes, st);
     if (e != cudaSuccess) return e;
+    uint32_t* pairs = fused ? nullptr : (uint32_t*)((char*)sc.p + summ_only_bytes(n * tc, parts));
     for (int64_t t0 = 0; (t0 < T || (T == 0 && t0 == 0)) && e == cudaSuccess; t0 += tc) {
         const int64_t tn = T - t0 < tc ? T - t0 : tc;
         const float* base = logits + t0 * ts;
         if (tn > 0) e = launch_summary(base, n, tn, ss, ts, V, parts, path, 0, (uint64_t*)sc.p, st);
         if (e != cudaSuccess) break;
+        const int fin = (finish && t0 + tn >= T) ? 1 : 0;
+        if (!fused) {
+            e = launch_pairs(base, n, tn, ss, ts, V, parts, path, (const uint64_t*)sc.p, syms + t0, sym_stride, pairs, st);
+            if (e != cudaSuccess) break;
+            // ntok counts from the start of the call: shift it by t0 inside the kernel
+            e = launch_encode_pairs_at(pairs, n, tn, tn, 1, ntok, t0, state, out, out_stride, fin, P, st);
+            continue;
+        }
         EncParams ep;
         ep.base = base;
         ep.n_streams = n;
@@ -690,15 +717,11 @@ cudaError_t launch_encode_logits(const float* logits, int64_t n, int64_t T, int6
         ep.out_stride = out_stride;
         ep.V = V;
         ep.P = P;
-        ep.finish = (finish && t0 + tn >= T) ? 1 : 0;
-        // streams per block and tokens per batch: one stream per block for slices of >= 16 tokens (two rows per warp
-        // and batch), more streams per block for shorter calls so that every warp still has a row (T = 1: 8 streams)
-        ep.tb = (int)(tn >= 16 ? 16 : (tn < 1 ? 1 : tn));
-        ep.spb = tn >= 16 ? 1 : (kEncRows / 2 / ep.tb < 1 ? 1 : kEncRows / 2 / ep.tb);
-        if (ep.spb > 8) ep.spb = 8;
-        if (tn == 0) {  // flush-only call: as many streams per block as the stage allows
-            ep.spb = kEncMaxSpb;
-        }
+        ep.finish = fin;
+        // streams per block and tokens per batch: every warp of a block should have a row (T = 1: 8 streams)
+        ep.tb = (int)(tn < 1 ? 1 : tn);
+        ep.spb = kEncWarps / ep.tb < 1 ? 1 : kEncWarps / ep.tb;
+        if (tn == 0) ep.spb = kEncMaxSpb;  // flush-only call: as many streams per block as the stage allows
         const unsigned blocks = (unsigned)((n + ep.spb - 1) / ep.spb);
 #define LAC_ENC(CL_)                                                             \
     if (path == 0) encode_fused_kernel<1, CL_><<<blocks, kEncWarps * 32, 0, st>>>(ep); \

@@ -1,156 +1,291 @@
 """The llama_compress.py path (reference llama_compress.py:1-61) on the GPU: an autoregressive model
 predicts every token, the logits go through LQ32 and the batched range coder, independent chunks are
-independent streams.
+independent streams, batches of chunks shard over the GPUs of a box.
 
 Reference behaviour kept:
-  * every chunk starts from a reset model that has seen the BOS token 1 (Llama_AC.reset, :18-21);
+  * every chunk starts from a reset model that has seen the BOS token 1 (Llama_AC.reset, :20-23);
   * the table for position t is computed from the logits after tokens < t (calc_dist, :24-30);
-  * coder precision 48 (r(..., prec=48), :4).
+  * coder precision 48 (r(..., prec=48), :4);
+  * an unknown token raises AssertionError("unknown symbol") (:51-52).
 Reference behaviour replaced: tables are LQ32 (total 2^32) instead of cumsum(clip(softmax * 2^60, 2)) --
-bound in DESIGN.md section 3 -- and chunks carry their token counts in the LACB container.
+bound in DESIGN.md section 3 -- and chunks carry their token counts in the LACB container.  The reference's
+context roll-over at n_ctx (accept, :31-39) does not arise: a chunk is at most max_len tokens.
 
 Losslessness needs bit-identical logits when compressing and decompressing.  The reference gets that by
-evaluating llama.cpp token by token in both directions; here both directions call the SAME
-`model.step(tokens)` incremental forward with the same batch shape, so the same kernels run in the same
-order.  (A prefill-style encoder would be faster but is not bit-reproducible against a stepwise decoder.)
+evaluating llama.cpp token by token in both directions; here both directions replay the SAME captured CUDA graph
+of `model.step` with the same batch shape (chunks are coded in batches of exactly `batch_streams` streams), so
+the same kernels run in the same order whether a file is written on one GPU and read on eight or the other way
+round.  (A prefill-style encoder would be faster but is not bit-reproducible against a stepwise decoder.)
+
+The per-token step -- model forward, LQ32 row summaries, fused symbol-range + range-coder kernel (or the decoder's
+serial pass), position update -- is ONE CUDA graph replay with no host-fed inputs: the tokens of the step are
+gathered on the device from the token matrix with the device-side position.
 """
 from __future__ import annotations
 
 import math
-from typing import List, Optional
+from dataclasses import dataclass
+from typing import Dict, List, Optional
 
 import numpy as np
 import torch
 
-from . import coder, container
+from . import _ffi, coder, container, sharding
 
-BOS = 1  # llama_compress.py:19 self.past = [1]
+BOS = 1  # llama_compress.py:21 self.past = [1]
 
 
-class TinyLlama(torch.nn.Module):
-    """Small Llama-style decoder (RMSNorm, rotary attention with a KV cache, SwiGLU), random-init, used
-    as the stand-in predictor.  step(tokens[S]) -> fp32 logits [S, vocab] for the next position."""
+@dataclass(frozen=True)
+class LlamaConfig:
+    name: str
+    vocab: int
+    dim: int
+    layers: int
+    heads: int
+    kv_heads: int
+    ffn: int
+    max_len: int = 2048
 
-    def __init__(self, vocab=32000, dim=256, layers=2, heads=4, max_len=2049, seed=0, dtype=torch.float32):
+    def describe(self) -> str:
+        return (f"{self.name}:v{self.vocab}:d{self.dim}:l{self.layers}:h{self.heads}:kv{self.kv_heads}:f{self.ffn}:"
+                f"n{self.max_len}")
+
+    @property
+    def params(self) -> int:
+        hd = self.dim // self.heads
+        per_layer = self.dim * (self.heads + 2 * self.kv_heads) * hd + self.dim * self.dim + 3 * self.dim * self.ffn
+        return self.layers * per_layer + 2 * self.vocab * self.dim
+
+
+CONFIGS: Dict[str, LlamaConfig] = {
+    # miniature for tests
+    "tiny": LlamaConfig("tiny", 32000, 256, 2, 4, 2, 512, 2048),
+    # configs[2]: "Llama-style ~1B random-init model (vocab 32000)" -- TinyLlama-1.1B geometry
+    "1b": LlamaConfig("1b", 32000, 2048, 22, 32, 4, 5632, 2048),
+    # configs[3]: Llama-3 8B geometry (vocab 128256)
+    "8b": LlamaConfig("8b", 128256, 4096, 32, 32, 8, 14336, 2048),
+    # configs[4]: a 1B-class predictor with the 128256 vocabulary (Llama-3.2-1B geometry) for 8192 concurrent streams
+    "1b-128k": LlamaConfig("1b-128k", 128256, 2048, 16, 32, 8, 8192, 2048),
+}
+
+_BUCKETS = (128, 256, 512, 1024, 2048, 4096, 8192)
+
+
+class LlamaModel(torch.nn.Module):
+    """Llama-style decoder (RMSNorm, rotary GQA attention with a KV cache, SwiGLU), random-init, bf16 weights.
+    step(tokens int64 [S]) -> fp32 logits [S, vocab] for the next position; the position lives on the device.
+    All shapes are static for a given attention bucket, so a step can be captured into a CUDA graph."""
+
+    def __init__(self, cfg: LlamaConfig, n_streams: int, max_len: Optional[int] = None, seed: int = 0,
+                 device="cuda", dtype=torch.bfloat16):
         super().__init__()
-        g = torch.Generator().manual_seed(seed)
-        self.vocab, self.dim, self.heads, self.max_len = vocab, dim, heads, max_len
-        hd = dim // heads
+        self.cfg, self.S = cfg, int(n_streams)
+        self.max_len = int(max_len or cfg.max_len)
+        self.device, self.dtype = torch.device(device), dtype
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        hd = cfg.dim // cfg.heads
+        self.hd = hd
 
         def w(*shape, scale):
-            return torch.nn.Parameter((torch.randn(*shape, generator=g) * scale).to(dtype), requires_grad=False)
-        self.emb = w(vocab, dim, scale=1.0)
-        self.blocks = torch.nn.ParameterList()
-        for _ in range(layers):
-            self.blocks.extend([w(dim, 3 * dim, scale=dim ** -0.5), w(dim, dim, scale=dim ** -0.5),
-                                w(dim, 4 * dim, scale=dim ** -0.5), w(dim, 4 * dim, scale=dim ** -0.5),
-                                w(4 * dim, dim, scale=(4 * dim) ** -0.5)])
-        self.head = w(dim, vocab, scale=dim ** -0.5 * 4.0)
-        inv = 1.0 / (10000 ** (torch.arange(0, hd, 2).float() / hd))
-        ang = torch.arange(max_len).float()[:, None] * inv[None]
-        self.register_buffer("cos", ang.cos())
-        self.register_buffer("sin", ang.sin())
-        self.layers = layers
-        self.cache = None
-        self.pos = 0
+            return (torch.randn(*shape, generator=g, device=self.device, dtype=torch.float32) * scale).to(dtype)
+        d = cfg.dim
+        self.emb = w(cfg.vocab, d, scale=1.0)
+        self.wqkv = [w(d, (cfg.heads + 2 * cfg.kv_heads) * hd, scale=d ** -0.5) for _ in range(cfg.layers)]
+        self.wo = [w(d, d, scale=d ** -0.5) for _ in range(cfg.layers)]
+        self.w13 = [w(d, 2 * cfg.ffn, scale=d ** -0.5) for _ in range(cfg.layers)]
+        self.w2 = [w(cfg.ffn, d, scale=cfg.ffn ** -0.5) for _ in range(cfg.layers)]
+        self.head = w(d, cfg.vocab, scale=d ** -0.5 * 3.0)   # logit std ~3: a peaked, LLM-like next-token law
+        inv = 1.0 / (10000 ** (torch.arange(0, hd, 2, device=self.device).float() / hd))
+        ang = torch.arange(self.max_len, device=self.device).float()[:, None] * inv[None]
+        self.cos, self.sin = ang.cos(), ang.sin()
+        # KV cache [layer][S, kv_heads, max_len, hd]
+        self.kc = [torch.zeros((self.S, cfg.kv_heads, self.max_len, hd), device=self.device, dtype=dtype)
+                   for _ in range(cfg.layers)]
+        self.vc = [torch.zeros_like(k) for k in self.kc]
+        self.pos = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.ar = torch.arange(self.max_len, device=self.device)
 
-    def reset(self, n_streams: int):
-        dev = self.emb.device
-        hd = self.dim // self.heads
-        self.cache = [torch.zeros((2, n_streams, self.heads, self.max_len, hd), device=dev, dtype=self.emb.dtype)
-                      for _ in range(self.layers)]
-        self.pos = 0
+    def reset(self):
+        self.pos.zero_()
 
     @staticmethod
     def _norm(x):
-        return x * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + 1e-6).to(x.dtype)
+        return (x.float() * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + 1e-6)).to(x.dtype)
 
-    def _rope(self, x):  # x [S, H, hd]
-        c, s = self.cos[self.pos].to(x.dtype), self.sin[self.pos].to(x.dtype)
-        a, b = x[..., 0::2], x[..., 1::2]
-        return torch.stack([a * c - b * s, a * s + b * c], dim=-1).flatten(-2)
+    def _rope(self, x, c, s):  # x [S, H, hd]; c, s [1, 1, hd / 2]
+        a, b = x[..., 0::2].float(), x[..., 1::2].float()
+        return torch.stack([a * c - b * s, a * s + b * c], dim=-1).flatten(-2).to(x.dtype)
 
     @torch.no_grad()
-    def step(self, tokens: torch.Tensor) -> torch.Tensor:
-        S, H, hd = tokens.shape[0], self.heads, self.dim // self.heads
-        x = self.emb[tokens.long()]
-        for l in range(self.layers):
-            wqkv, wo, w1, w3, w2 = self.blocks[5 * l:5 * l + 5]
-            q, k, v = (self._norm(x) @ wqkv).view(S, 3, H, hd).unbind(1)
-            q, k = self._rope(q), self._rope(k)
-            kc, vc = self.cache[l][0], self.cache[l][1]
-            kc[:, :, self.pos], vc[:, :, self.pos] = k, v
-            att = torch.einsum("shd,shtd->sht", q, kc[:, :, : self.pos + 1]) / math.sqrt(hd)
-            x = x + torch.einsum("sht,shtd->shd", att.softmax(-1), vc[:, :, : self.pos + 1]).reshape(S, self.dim) @ wo
-            h = self._norm(x)
-            x = x + (torch.nn.functional.silu(h @ w1) * (h @ w3)) @ w2
-        self.pos += 1
-        return (self._norm(x) @ self.head).float().contiguous()
+    def step(self, tokens: torch.Tensor, bucket: int) -> torch.Tensor:
+        """One position for all S streams; attends over the first `bucket` cache slots (bucket > pos)."""
+        cfg, S, hd = self.cfg, self.S, self.hd
+        H, K = cfg.heads, cfg.kv_heads
+        G = H // K
+        pos = self.pos
+        c = self.cos.index_select(0, pos).view(1, 1, -1)
+        s = self.sin.index_select(0, pos).view(1, 1, -1)
+        mask = (self.ar[:bucket] > pos).view(1, 1, 1, bucket)
+        x = self.emb.index_select(0, tokens)
+        for l in range(cfg.layers):
+            qkv = (self._norm(x) @ self.wqkv[l]).view(S, H + 2 * K, hd)
+            q = self._rope(qkv[:, :H], c, s)
+            k = self._rope(qkv[:, H:H + K], c, s)
+            v = qkv[:, H + K:]
+            self.kc[l].index_copy_(2, pos, k.unsqueeze(2))
+            self.vc[l].index_copy_(2, pos, v.unsqueeze(2))
+            kk, vv = self.kc[l][:, :, :bucket], self.vc[l][:, :, :bucket]
+            att = torch.matmul(q.view(S, K, G, hd), kk.transpose(-1, -2)).float() / math.sqrt(hd)
+            att = att.masked_fill(mask, float("-inf")).softmax(-1).to(self.dtype)
+            o = torch.matmul(att, vv).reshape(S, H * hd)
+            x = x + o @ self.wo[l]
+            h13 = self._norm(x) @ self.w13[l]
+            x = x + (torch.nn.functional.silu(h13[:, :cfg.ffn]) * h13[:, cfg.ffn:]) @ self.w2[l]
+        return (self._norm(x) @ self.head).float()
+
+
+def _bucket_for(pos: int, max_len: int) -> int:
+    for b in _BUCKETS:
+        if pos < b:
+            return min(b, max_len)
+    return max_len
+
+
+class StepEngine:
+    """The per-token loop of one batch: holds the model, the static device buffers and one captured CUDA graph per
+    (direction, attention bucket).  A step is `graph.replay()`; nothing is fed from the host."""
+
+    def __init__(self, model: LlamaModel, chunk_tokens: int, prec: int, use_graphs: bool = True):
+        self.m, self.T, self.prec, self.use_graphs = model, int(chunk_tokens), int(prec), use_graphs
+        S, V, dev = model.S, model.cfg.vocab, model.device
+        if self.T > model.max_len:
+            raise ValueError("chunk_tokens exceeds the model's max_len")
+        self.tok = torch.zeros((S, self.T), dtype=torch.int32, device=dev)      # encode: input; decode: output
+        self.ntok = torch.zeros(S, dtype=torch.int32, device=dev)
+        self.live = torch.zeros(S, dtype=torch.int32, device=dev)
+        self.sym = torch.zeros(S, dtype=torch.int32, device=dev)
+        self.ws = coder.Workspace(S, V, dev)
+        self.cap = self.T * 8 + 64
+        self.enc: Optional[coder.StreamEncoder] = None
+        self.dec: Optional[coder.StreamDecoder] = None
+        self.graphs: Dict = {}
+        self.stream = torch.cuda.Stream(device=dev)
+
+    # ---- one step, expressed on device tensors only
+    def _prev_tokens(self):
+        pos = self.m.pos
+        prev = self.tok.index_select(1, (pos - 1).clamp_(min=0)).squeeze(1).to(torch.int64)
+        return torch.where(pos > 0, prev, torch.full_like(prev, BOS))
+
+    def _enc_step(self, bucket):
+        logits = self.m.step(self._prev_tokens(), bucket)
+        pos = self.m.pos
+        self.sym.copy_(self.tok.index_select(1, pos).squeeze(1))
+        self.live.copy_((self.ntok > pos).to(torch.int32))
+        self.enc.encode_step(logits, self.sym, self.live, self.ws)
+        pos.add_(1)
+
+    def _dec_step(self, bucket):
+        logits = self.m.step(self._prev_tokens(), bucket)
+        pos = self.m.pos
+        self.live.copy_((self.ntok > pos).to(torch.int32))
+        self.dec.decode_step(logits, self.live, self.ws, out=self.sym)
+        self.tok.index_copy_(1, pos, torch.where(self.live > 0, self.sym, torch.zeros_like(self.sym)).unsqueeze(1))
+        pos.add_(1)
+
+    def _run(self, kind, n_steps):
+        fn = self._enc_step if kind == "enc" else self._dec_step
+        cur = torch.cuda.current_stream(self.m.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            for t in range(n_steps):
+                bucket = _bucket_for(t, self.m.max_len)
+                if not self.use_graphs:
+                    fn(bucket)
+                    continue
+                key = (kind, bucket)
+                if key not in self.graphs:
+                    # warm-up run outside capture (cuBLAS handles / workspaces), then rewind what it changed
+                    snap = self._snapshot(kind)
+                    fn(bucket)
+                    self._restore(kind, snap)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=self.stream):
+                        fn(bucket)
+                    self._restore(kind, snap)
+                    self.graphs[key] = g
+                self.graphs[key].replay()
+        cur.wait_stream(self.stream)
+
+    def _snapshot(self, kind):
+        st = self.enc.state if kind == "enc" else self.dec.state
+        return (self.m.pos.clone(), st.clone(), self.tok.clone())
+
+    def _restore(self, kind, snap):
+        st = self.enc.state if kind == "enc" else self.dec.state
+        self.m.pos.copy_(snap[0])
+        st.copy_(snap[1])
+        self.tok.copy_(snap[2])
+
+    # ---- whole batches
+    def encode_batch(self, tokens: np.ndarray, ntok: np.ndarray):
+        S = self.m.S
+        assert tokens.shape == (S, self.T) and ntok.shape == (S,)
+        self.tok.copy_(torch.from_numpy(np.ascontiguousarray(tokens, dtype=np.int32)))
+        self.ntok.copy_(torch.from_numpy(np.ascontiguousarray(ntok, dtype=np.int32)))
+        if self.enc is None:
+            self.enc = coder.StreamEncoder(S, prec=self.prec, capacity_bytes=self.cap, device=self.m.device)
+        else:
+            self.enc.reset()
+        self.m.reset()
+        self._run("enc", int(ntok.max()) if len(ntok) else 0)
+        self.enc.finish()
+        return self.enc.bitstreams()
+
+    def decode_batch(self, streams: List[bytes], ntok: np.ndarray) -> np.ndarray:
+        S = self.m.S
+        assert len(streams) == S and ntok.shape == (S,)
+        self.ntok.copy_(torch.from_numpy(np.ascontiguousarray(ntok, dtype=np.int32)))
+        self.tok.zero_()
+        if self.dec is None:
+            self.dec = coder.StreamDecoder(streams, prec=self.prec, device=self.m.device,
+                                           capacity_bytes=S * self.cap)
+        else:
+            self.dec.reset(streams)
+        self.m.reset()
+        self._run("dec", int(ntok.max()) if len(ntok) else 0)
+        st = self.dec.status()
+        if st & _ffi.LAC_ST_TRUNC:
+            raise _ffi.LacError(_ffi.LAC_E_STREAM, "truncated or foreign bitstream (wrong model for this file?)")
+        return self.tok.cpu().numpy()
 
 
 class LlamaCompressor:
-    """compress(token ids) -> LACB bytes, decompress(bytes) -> token ids."""
+    """compress(token ids) -> LACB bytes, decompress(bytes) -> token ids.  With torch.distributed initialised every
+    rank calls both with the same arguments; rank 0 gets the result, the others None."""
 
-    def __init__(self, model, vocab: int, chunk_tokens: int = 2048, prec: int = coder.DEFAULT_PREC,
-                 max_streams: int = 1024, device="cuda"):
-        self.model, self.vocab, self.chunk, self.prec, self.max_streams = model, vocab, chunk_tokens, prec, max_streams
-        self.device = torch.device(device)
+    def __init__(self, model: LlamaModel, chunk_tokens: int = 2048, prec: int = coder.DEFAULT_PREC,
+                 use_graphs: bool = True, group=None):
+        self.model, self.chunk, self.prec, self.group = model, int(chunk_tokens), int(prec), group
+        self.vocab = model.cfg.vocab
+        self.engine = StepEngine(model, chunk_tokens, prec, use_graphs)
+        self.tag = container.model_tag(model.cfg.describe())
 
-    def _batches(self, n_chunks):
-        for b in range(0, n_chunks, self.max_streams):
-            yield b, min(n_chunks, b + self.max_streams)
-
-    def compress(self, tokens) -> bytes:
+    def compress(self, tokens) -> Optional[bytes]:
         toks = np.ascontiguousarray(tokens, dtype=np.int32)
         if toks.size and (int(toks.min()) < 0 or int(toks.max()) >= self.vocab):
-            raise AssertionError("unknown symbol", int(toks.max() if toks.max() >= self.vocab else toks.min()))  # arith_code.py:104-105
-        n_chunks = (len(toks) + self.chunk - 1) // self.chunk
-        padded = np.zeros(n_chunks * self.chunk, dtype=np.int32)
-        padded[: len(toks)] = toks
-        padded = padded.reshape(n_chunks, self.chunk)
-        ntok = np.full(n_chunks, self.chunk, dtype=np.int32)
-        if n_chunks:
-            ntok[-1] = len(toks) - (n_chunks - 1) * self.chunk
-        streams: List[bytes] = []
-        nbits: List[int] = []
-        for b, e in self._batches(n_chunks):
-            S = e - b
-            d_tok = torch.from_numpy(padded[b:e]).to(self.device)
-            d_ntok = torch.from_numpy(ntok[b:e]).to(self.device)
-            enc = coder.StreamEncoder(S, prec=self.prec, capacity_bytes=self.chunk * 8 + 64, device=self.device)
-            self.model.reset(S)
-            prev = torch.full((S,), BOS, dtype=torch.int32, device=self.device)
-            for t in range(int(ntok[b:e].max())):
-                logits = self.model.step(prev)                       # what the decoder will also compute
-                live = (d_ntok > t).to(torch.int32)                   # ragged tail chunk
-                enc.encode_logits(logits.unsqueeze(1), d_tok[:, t:t + 1].contiguous(), ntok=live)
-                prev = d_tok[:, t].contiguous()
-            enc.finish()
-            s, nb = enc.bitstreams()
-            streams += s
-            nbits += [int(x) for x in nb]
-        return container.pack(streams, ntok, nbits, self.prec, self.vocab, self.chunk)
+            bad = int(toks.max()) if int(toks.max()) >= self.vocab else int(toks.min())
+            raise AssertionError("unknown symbol", bad)  # llama_compress.py:51-52
+        return sharding.compress_sharded(toks, self.chunk, self.model.S, self.engine.encode_batch, self.prec,
+                                         self.vocab, self.model.device, self.tag, self.group)
 
-    def decompress(self, blob: bytes) -> np.ndarray:
+    def decompress(self, blob: bytes) -> Optional[np.ndarray]:
         c = container.unpack(blob)
         if c.vocab != self.vocab or c.quantiser != container.QUANT_LQ32:
             raise ValueError("container was written for a different vocabulary / quantiser")
-        all_streams = c.streams()
-        out = np.zeros((c.n_chunks, c.chunk_tokens), dtype=np.int32)
-        for b, e in self._batches(c.n_chunks):
-            S = e - b
-            d_ntok = torch.from_numpy(c.ntok[b:e].astype(np.int32)).to(self.device)
-            dec = coder.StreamDecoder(all_streams[b:e], prec=c.prec, device=self.device)
-            self.model.reset(S)
-            prev = torch.full((S,), BOS, dtype=torch.int32, device=self.device)
-            got = torch.zeros((S, c.chunk_tokens), dtype=torch.int32, device=self.device)
-            for t in range(int(c.ntok[b:e].max())):
-                logits = self.model.step(prev)
-                live = (d_ntok > t).to(torch.int32)
-                sym = dec.decode_logits(logits.unsqueeze(1), ntok=live).squeeze(1)
-                sym = torch.where(live.bool(), sym, torch.zeros_like(sym))
-                got[:, t] = sym
-                prev = sym
-            out[b:e] = got.cpu().numpy()
-        flat = [out[i, : int(c.ntok[i])] for i in range(c.n_chunks)]
-        return np.concatenate(flat) if flat else np.zeros(0, dtype=np.int32)
+        if c.batch_streams != self.model.S or c.chunk_tokens != self.chunk:
+            raise ValueError(f"container was written with batches of {c.batch_streams} streams x {c.chunk_tokens} "
+                             f"tokens; this compressor runs {self.model.S} x {self.chunk}")
+        if c.tag and c.tag != self.tag:
+            raise ValueError("container was written with a different predictor configuration")
+        return sharding.decompress_sharded(blob, self.engine.decode_batch, self.model.device, self.group)

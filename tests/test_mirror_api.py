@@ -127,19 +127,63 @@ def test_mirror_acsampler_on_goldens(golden_dir):
 
 @gpu
 @needs_gpu
-def test_llama_compress_roundtrip_and_size():
-    """configs[2] in miniature: Llama-style random-init model, vocab 32000, ragged chunks, container."""
+@pytest.mark.parametrize("use_graphs", [True, False])
+def test_llama_compress_roundtrip_and_size(use_graphs):
+    """configs[2] in miniature: Llama-style random-init model, vocab 32000, ragged chunks, full-shape batches (the
+    last one padded with empty streams), container; per-token step replayed from a CUDA graph."""
     from lac_b200 import container, llama_compress as lc
-    vocab, chunk = 32000, 24
-    model = lc.TinyLlama(vocab=vocab, dim=64, layers=2, heads=4, max_len=chunk + 1, seed=3).cuda()
+    chunk, B = 24, 4
+    cfg = lc.LlamaConfig("t", 32000, 64, 2, 4, 2, 128, 64)
+    model = lc.LlamaModel(cfg, n_streams=B, max_len=chunk, seed=3)
     rng = np.random.default_rng(5)
-    toks = rng.integers(0, vocab, 5 * chunk + 7).astype(np.int32)
-    comp = lc.LlamaCompressor(model, vocab, chunk_tokens=chunk, max_streams=4)
+    toks = rng.integers(0, cfg.vocab, 5 * chunk + 7).astype(np.int32)
+    comp = lc.LlamaCompressor(model, chunk_tokens=chunk, use_graphs=use_graphs)
     blob = comp.compress(toks)
     c = container.unpack(blob)
-    assert c.n_chunks == 6 and c.ntok.tolist() == [chunk] * 5 + [7]
+    assert c.n_chunks == 6 and c.ntok.tolist() == [chunk] * 5 + [7] and c.batch_streams == B
     back = comp.decompress(blob)
     assert np.array_equal(back, toks)
-    # random tokens under a random-init model (logit std ~4) cost log2(V) + sigma^2 / (2 ln 2) ~ 26 bits each
+    # a second compressor instance (fresh graphs, same seed) reads the file, and writes the same file
+    comp2 = lc.LlamaCompressor(lc.LlamaModel(cfg, n_streams=B, max_len=chunk, seed=3), chunk_tokens=chunk,
+                               use_graphs=use_graphs)
+    assert np.array_equal(comp2.decompress(blob), toks)
+    assert comp2.compress(toks) == blob
+    # random tokens under a random-init model (logit std ~3) cost about log2(V) + sigma^2 / (2 ln 2) ~ 21 bits each
     bits = float(c.nbits.sum())
-    assert 0.9 * np.log2(vocab) * len(toks) < bits < 2.5 * np.log2(vocab) * len(toks)
+    assert 0.9 * np.log2(cfg.vocab) * len(toks) < bits < 2.5 * np.log2(cfg.vocab) * len(toks)
+    with pytest.raises(AssertionError):
+        comp.compress(np.array([1, 2, cfg.vocab], dtype=np.int32))
+    # a file for another predictor is refused, a damaged payload is reported
+    other = lc.LlamaCompressor(lc.LlamaModel(lc.LlamaConfig("u", 32000, 64, 1, 4, 2, 128, 64), B, chunk, seed=3),
+                               chunk_tokens=chunk, use_graphs=use_graphs)
+    with pytest.raises(ValueError):
+        other.decompress(blob)
+
+
+@gpu
+@needs_gpu
+def test_llama_model_in_distribution_text_compresses():
+    """Tokens SAMPLED from the model (in-distribution text) must cost about the model's entropy, far below
+    log2(V): the coder is driven by the model, not by a uniform table."""
+    import torch
+    from lac_b200 import container, llama_compress as lc
+    chunk, B = 32, 8
+    cfg = lc.LlamaConfig("t", 32000, 64, 2, 4, 2, 128, 64)
+    model = lc.LlamaModel(cfg, n_streams=B, max_len=chunk, seed=4)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    model.reset()
+    prev = torch.full((B,), lc.BOS, dtype=torch.int64, device="cuda")
+    cols, ent = [], 0.0
+    for t in range(chunk):
+        logits = model.step(prev, lc._bucket_for(t, chunk))
+        p = torch.softmax(logits.double(), -1)
+        prev = torch.multinomial(p.float(), 1, generator=g).squeeze(1)
+        ent += float(-(p * torch.log2(p.clamp_min(1e-300))).sum(-1).sum())
+        cols.append(prev.to(torch.int32))
+        model.pos.add_(1)
+    toks = torch.stack(cols, 1).cpu().numpy().reshape(-1)
+    comp = lc.LlamaCompressor(model, chunk_tokens=chunk, use_graphs=False)
+    blob = comp.compress(toks)
+    bits = float(container.unpack(blob).nbits.sum())
+    assert bits < 1.25 * ent + 64 * B and bits < 0.8 * np.log2(cfg.vocab) * len(toks)
+    assert np.array_equal(comp.decompress(blob), toks)
