@@ -430,6 +430,213 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------ model-in-the-loop workloads (configs[2..4])
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    return rank, world, local, dev
+
+
+def _timed(fn, dev, world):
+    """fn() bracketed by barrier + synchronize on both sides; seconds, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = fn()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return out, dt
+
+
+def _step_split(engine, bucket, reps=20):
+    """ms per token step at one attention bucket: model forward alone vs the whole encode / decode step (model +
+    LQ32 summary + coder kernels), each replayed from its own CUDA graph and timed with CUDA events."""
+    import torch
+    from lac_b200 import coder, llama_compress as lc
+    m = engine.m
+    S, dev = m.S, m.device
+    if engine.enc is None:
+        engine.enc = coder.StreamEncoder(S, prec=engine.prec, capacity_bytes=engine.cap, device=dev)
+    engine.enc.reset()
+    enc = engine.enc
+    engine.ntok.fill_(engine.T)
+    res = {}
+    prev = torch.full((S,), lc.BOS, dtype=torch.int64, device=dev)
+
+    def model_only():
+        m.step(prev, bucket)
+
+    def enc_step():
+        engine._enc_step(bucket)
+        m.pos.sub_(1)
+
+    st = torch.cuda.Stream(device=dev)
+    st.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(st):
+        for name, fn in (("model_ms", model_only), ("encode_step_ms", enc_step)):
+            m.reset()
+            fn()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                fn()
+            for _ in range(3):
+                g.replay()
+            b, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b.record(st)
+            for _ in range(reps):
+                g.replay()
+            e.record(st)
+            e.synchronize()
+            res[name] = b.elapsed_time(e) / reps
+            if name == "encode_step_ms":
+                enc.reset()
+    torch.cuda.current_stream(dev).wait_stream(st)
+    torch.cuda.synchronize()
+    res["coder_share_of_encode_step"] = max(0.0, 1.0 - res["model_ms"] / res["encode_step_ms"])
+    res["bucket"] = bucket
+    return res
+
+
+def run_llama(args):
+    """configs[2] / configs[3]: the llama_compress.py path.  Synthetic text (uniform random token ids), random-init
+    weights of the named geometry, chunks of --chunk-tokens tokens coded in model batches of --batch-streams
+    streams, batches sharded over the ranks, ONE gather of the index and one of the payload into a LACB file on
+    rank 0, then decompressed the same way and compared."""
+    import torch
+    import torch.distributed as dist
+    from lac_b200 import container, llama_compress as lc
+    rank, world, local, dev = _dist_setup()
+    cfg = lc.CONFIGS[args.model]
+    n_tokens = int(args.text_mb * (1 << 20) / 4)          # ~4 bytes of text per token
+    if args.tokens:
+        n_tokens = args.tokens
+    rng = np.random.default_rng(2024)
+    toks = rng.integers(0, cfg.vocab, n_tokens).astype(np.int32)
+    model = lc.LlamaModel(cfg, n_streams=args.batch_streams, max_len=args.chunk_tokens, seed=0, device=dev)
+    comp = lc.LlamaCompressor(model, chunk_tokens=args.chunk_tokens, use_graphs=not args.no_graphs)
+    # warm-up: one short job (captures every attention bucket's graphs in both directions)
+    wtoks = toks[: args.batch_streams * args.chunk_tokens * world]
+    wb = comp.compress(wtoks[: args.chunk_tokens * world * 2] if args.quick_warmup else wtoks)
+    if world > 1:
+        box = [wb]
+        dist.broadcast_object_list(box, src=0)
+        wb = box[0]
+    comp.decompress(wb)
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    blob, t_enc = _timed(lambda: comp.compress(toks), dev, world)
+    if world > 1:
+        box = [blob]
+        dist.broadcast_object_list(box, src=0)
+        blob = box[0]
+    back, t_dec = _timed(lambda: comp.decompress(blob), dev, world)
+    clk = clocks.stop() if rank == 0 else None
+    split = _step_split(comp.engine, lc._bucket_for(args.chunk_tokens // 2, args.chunk_tokens)) if rank == 0 else None
+    if rank == 0:
+        assert np.array_equal(back, toks), "llama path did not round-trip"
+        c = container.unpack(blob)
+        n_chunks = c.n_chunks
+        line = {
+            "workload": "llama", "metric": METRIC, "value": n_tokens / (t_enc + t_dec), "unit": UNIT, "n_gpus": world,
+            "higher_is_better": True, "scaling": "strong", "data": "synthetic (uniform random token ids)",
+            "dtype": "bf16 model forward, f32 logits -> u32/u64 coder",
+            "config": {"workload": f"llama_compress path, {cfg.name} random-init model ({cfg.params / 1e9:.2f} B parameters, "
+                                   f"vocab {cfg.vocab}), {n_tokens} tokens (~{n_tokens * 4 / (1 << 20):.0f} MB of text) in "
+                                   f"{args.chunk_tokens}-token chunks, model batches of {args.batch_streams} streams sharded over "
+                                   f"{world} GPU(s), one LACB file",
+                       "model": cfg.describe(), "chunks": n_chunks, "batch_streams": args.batch_streams,
+                       "cuda_graphs": not args.no_graphs},
+            "encode_tokens_per_s": n_tokens / t_enc, "decode_tokens_per_s": n_tokens / t_dec,
+            "encode_s": t_enc, "decode_s": t_dec, "lossless": True,
+            "bits_per_token": float(c.nbits.sum()) / max(n_tokens, 1), "container_bytes": len(blob),
+            "step_split": split, "clocks": clk,
+            "collectives": "one all_gather of (tokens, bits) per chunk + one all_gather of the payload per job; none in the coding loop",
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_stress(args):
+    """configs[4]: decode-heavy stress -- --streams concurrent streams (default 8192), vocab 128256, sequential
+    per-token decode with the model in the loop, lossless round trip verified."""
+    import torch
+    from lac_b200 import llama_compress as lc
+    rank, world, local, dev = _dist_setup()
+    cfg = lc.CONFIGS[args.model]
+    S, T = args.stress_streams, args.stress_tokens
+    rng = np.random.default_rng(7 + rank)
+    toks = rng.integers(0, cfg.vocab, (S, T)).astype(np.int32)
+    ntok = np.full(S, T, dtype=np.int32)
+    model = lc.LlamaModel(cfg, n_streams=S, max_len=T, seed=0, device=dev)
+    eng = lc.StepEngine(model, T, PREC, use_graphs=not args.no_graphs)
+    eng.encode_batch(toks[:, :T], ntok)                      # warm-up (graph capture) + the streams to decode
+    (streams, nbits), t_enc = _timed(lambda: eng.encode_batch(toks, ntok), dev, world)
+    eng.decode_batch(streams, ntok)                          # warm-up (graph capture)
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    back, t_dec = _timed(lambda: eng.decode_batch(streams, ntok), dev, world)
+    clk = clocks.stop() if rank == 0 else None
+    assert np.array_equal(back, toks), "stress decode did not round-trip"
+    # per-step latency of the decoder call alone (summary pass + serial pass) on this shape, CUDA events
+    from lac_b200 import _ffi, coder
+    L = _ffi.lib()
+    logits = torch.randn((S, 1, cfg.vocab), device=dev) * 3.0
+    dec = coder.StreamDecoder(streams, prec=PREC, device=dev)
+    out = torch.zeros((S, 1), dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    reps = 20
+    for k in range(reps + 3):
+        if k == 3:
+            ev[0].record()
+        _ffi.check(L.lac_ac_decode_logits_f32(logits.data_ptr(), S, 1, cfg.vocab, cfg.vocab, cfg.vocab, None,
+                                              dec.state.data_ptr(), dec.bytes.data_ptr(), dec.offsets.data_ptr(),
+                                              out.data_ptr(), 1, PREC, eng.ws.ptr, eng.ws.nbytes, st))
+    ev[1].record()
+    torch.cuda.synchronize()
+    dec_call_ms = ev[0].elapsed_time(ev[1]) / reps
+    peak, _ = peaks()
+    if rank == 0:
+        line = {
+            "workload": "stress", "metric": "decoded_tokens_per_s", "value": world * S * T / t_dec, "unit": UNIT,
+            "n_gpus": world, "higher_is_better": True, "scaling": "weak", "data": "synthetic (uniform random token ids)",
+            "config": {"workload": f"decode-heavy stress: {S} concurrent streams x {T} tokens, vocab {cfg.vocab}, sequential "
+                                   f"per-token decode with the {cfg.name} model in the loop, lossless round trip verified",
+                       "model": cfg.describe(), "cuda_graphs": not args.no_graphs},
+            "decode_s": t_dec, "encode_s": t_enc, "ms_per_token_step": t_dec / T * 1e3, "lossless": True,
+            "bits_per_token": float(np.sum(nbits)) / (S * T),
+            "decoder_call": {"api": "lac_ac_decode_logits_f32, T = 1", "ms": dec_call_ms,
+                             "logits_bytes": S * cfg.vocab * 4,
+                             "achieved_gbs": S * cfg.vocab * 4 / (dec_call_ms * 1e-3) / 1e9,
+                             "frac_of_measured_hbm_peak": S * cfg.vocab * 4 / (dec_call_ms * 1e-3) / 1e9 / peak},
+            "clocks": clk,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -447,10 +654,24 @@ def main():
     ap.add_argument("--no-v128", action="store_true")
     ap.add_argument("--v128-tokens", type=int, default=256)
     ap.add_argument("--v128-jobs", type=int, default=100)
+    # model-in-the-loop workloads (extra lines, not the driver's headline): configs[2] / [3] / [4]
+    ap.add_argument("--workload", default="coder", choices=["coder", "llama", "stress"])
+    ap.add_argument("--model", default="1b", help="lac_b200.llama_compress.CONFIGS key: tiny, 1b, 8b, 1b-128k")
+    ap.add_argument("--text-mb", type=float, default=16.0)
+    ap.add_argument("--tokens", type=int, default=0, help="override the token count derived from --text-mb")
+    ap.add_argument("--batch-streams", type=int, default=256)
+    ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--quick-warmup", action="store_true")
+    ap.add_argument("--stress-streams", type=int, default=8192)
+    ap.add_argument("--stress-tokens", type=int, default=64)
     args = ap.parse_args()
     globals().update(VOCAB=args.vocab, STREAMS=args.streams, SLICE=args.slice, CHUNK_TOKENS=args.chunk_tokens)
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "llama":
+        run_llama(args)
+    elif args.workload == "stress":
+        run_stress(args)
     else:
         run_gpu(args)
 
