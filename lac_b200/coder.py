@@ -207,6 +207,14 @@ class StreamEncoder:
                                           2 if finish == "safe" else int(bool(finish)), self.prec, _cur_stream()))
         self.finished = self.finished or bool(finish)
 
+    def acs_flush(self, safe: bool = False):
+        """ACSampler.flush_compress (arithmetic_coding.py:50-56) on every stream, no token coded."""
+        one = torch.ones(1, dtype=torch.int64, device=self.device)
+        none = torch.empty((self.n, 0), dtype=torch.int32, device=self.device)
+        check(lib().lac_acs_encode_tables(one.data_ptr(), 1, 0, 0, none.data_ptr(), 0, self.n, 0, None,
+                                          self.state.data_ptr(), self.out.data_ptr(), self.cap, 2 if safe else 1,
+                                          self.prec, _cur_stream()))
+
     def finish(self):
         if not self.finished:
             empty = torch.empty((self.n, 0, 2), dtype=torch.int32, device=self.device)
@@ -289,14 +297,17 @@ class StreamDecoder:
                       ws: Optional[Workspace] = None, out: Optional[torch.Tensor] = None,
                       check_status: bool = True) -> torch.Tensor:
         """logits [n_streams, T, V] fp32 -> symbols int32 [n_streams, T] (row summaries, then search + update).
+        logits [1, T, V] is shared by all streams (stream stride 0).
         Raises LacError(LAC_E_STREAM) for a truncated / foreign stream unless check_status=False (a per-token loop
         checks once at the end with status())."""
         _need_cuda(logits, "logits", torch.float32)
         S, T, V = logits.shape
-        if S != self.n:
-            raise LacError(_ffi.LAC_E_ARG, "logits must be [n_streams, T, V]")
+        if S != self.n and S != 1:
+            raise LacError(_ffi.LAC_E_ARG, "logits must be [n_streams, T, V] (or [1, T, V], shared)")
+        stream_stride = T * V if S == self.n else 0
+        S = self.n
         syms = out if out is not None else torch.zeros((S, T), dtype=torch.int32, device=self.device)
-        check(lib().lac_ac_decode_logits_f32(logits.data_ptr(), S, T, T * V, V, V,
+        check(lib().lac_ac_decode_logits_f32(logits.data_ptr(), S, T, stream_stride, V, V,
                                              ntok.data_ptr() if ntok is not None else None, self.state.data_ptr(),
                                              self.bytes.data_ptr(), self.offsets.data_ptr(), syms.data_ptr(),
                                              syms.stride(0), self.prec, *_ws(ws), _cur_stream()))
@@ -318,7 +329,7 @@ class StreamDecoder:
         return int(flag.item()) & 0xFFFFFFFF
 
     def decode_tables(self, dist: torch.Tensor, minp: torch.Tensor, T: int, ntok: Optional[torch.Tensor] = None,
-                      wrap64: bool = False) -> torch.Tensor:
+                      wrap64: bool = False, check_status: bool = True) -> torch.Tensor:
         _need_cuda(dist, "dist", torch.int64)
         _need_cuda(minp, "minp", torch.int64)
         V, ss, ts, mss, mts = _table_strides(dist, minp, self.n, T)
@@ -327,19 +338,23 @@ class StreamDecoder:
                                          ntok.data_ptr() if ntok is not None else None, self.state.data_ptr(),
                                          self.bytes.data_ptr(), self.offsets.data_ptr(), syms.data_ptr(), T,
                                          self.prec, _ffi.LAC_F_WRAP64 if wrap64 else 0, _cur_stream()))
-        self._check_status()
+        if check_status:
+            self._check_status()
         return syms
 
-    def decode_uniform(self, n_symbols: int, T: int, ntok: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def decode_uniform(self, n_symbols: int, T: int, ntok: Optional[torch.Tensor] = None,
+                       check_status: bool = True) -> torch.Tensor:
         """Decoder for encode_uniform streams: the symbol whose floor-mapped range holds the code value."""
         syms = torch.zeros((self.n, T), dtype=torch.int32, device=self.device)
         check(lib().lac_ac_decode_uniform(self.n, T, ntok.data_ptr() if ntok is not None else None, int(n_symbols),
                                           self.state.data_ptr(), self.bytes.data_ptr(), self.offsets.data_ptr(),
                                           syms.data_ptr(), T, self.prec, _cur_stream()))
-        self._check_status()
+        if check_status:
+            self._check_status()
         return syms
 
-    def acs_decode_tables(self, cdf: torch.Tensor, T: int, ntok: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def acs_decode_tables(self, cdf: torch.Tensor, T: int, ntok: Optional[torch.Tensor] = None,
+                          check_status: bool = True) -> torch.Tensor:
         _need_cuda(cdf, "cdf", torch.int64)
         V, ss, ts, _, _ = _table_strides(cdf, None, self.n, T)
         syms = torch.zeros((self.n, T), dtype=torch.int32, device=self.device)
@@ -347,7 +362,8 @@ class StreamDecoder:
                                           ntok.data_ptr() if ntok is not None else None, self.state.data_ptr(),
                                           self.bytes.data_ptr(), self.offsets.data_ptr(), syms.data_ptr(), T,
                                           self.prec, _cur_stream()))
-        self._check_status()
+        if check_status:
+            self._check_status()
         return syms
 
     def _check_status(self):

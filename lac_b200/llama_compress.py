@@ -97,7 +97,8 @@ class LlamaModel(torch.nn.Module):
         self.head = w(d, cfg.vocab, scale=d ** -0.5 * 3.0)   # logit std ~3: a peaked, LLM-like next-token law
         inv = 1.0 / (10000 ** (torch.arange(0, hd, 2, device=self.device).float() / hd))
         ang = torch.arange(self.max_len, device=self.device).float()[:, None] * inv[None]
-        self.cos, self.sin = ang.cos(), ang.sin()
+        self.cos = torch.cat([ang.cos(), ang.cos()], -1).to(dtype)    # rotate-half form, [max_len, hd]
+        self.sin = torch.cat([ang.sin(), ang.sin()], -1).to(dtype)
         # KV cache [layer][S, kv_heads, max_len, hd]
         self.kc = [torch.zeros((self.S, cfg.kv_heads, self.max_len, hd), device=self.device, dtype=dtype)
                    for _ in range(cfg.layers)]
@@ -108,37 +109,37 @@ class LlamaModel(torch.nn.Module):
     def reset(self):
         self.pos.zero_()
 
-    @staticmethod
-    def _norm(x):
-        return (x.float() * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + 1e-6)).to(x.dtype)
+    def _norm(self, x):
+        return torch.nn.functional.rms_norm(x, (x.shape[-1],), eps=1e-6)
 
-    def _rope(self, x, c, s):  # x [S, H, hd]; c, s [1, 1, hd / 2]
-        a, b = x[..., 0::2].float(), x[..., 1::2].float()
-        return torch.stack([a * c - b * s, a * s + b * c], dim=-1).flatten(-2).to(x.dtype)
+    @staticmethod
+    def _rope(x, c, s):  # x [S, heads, hd]; c, s [1, 1, hd]
+        half = x.shape[-1] // 2
+        rot = torch.cat([-x[..., half:], x[..., :half]], -1)
+        return x * c + rot * s
 
     @torch.no_grad()
     def step(self, tokens: torch.Tensor, bucket: int) -> torch.Tensor:
-        """One position for all S streams; attends over the first `bucket` cache slots (bucket > pos)."""
+        """One position for all S streams; attends over the first `bucket` cache slots (bucket > pos).  The
+        attention is torch's scaled_dot_product_attention over the KV-cache slice with a position mask (measured
+        against a bmm formulation and flash_attn_with_kvcache in tools/attn_bench.py: 0.10 vs 0.29 / 0.19 ms per
+        layer at 256 streams x 2048 positions, deterministic)."""
         cfg, S, hd = self.cfg, self.S, self.hd
         H, K = cfg.heads, cfg.kv_heads
-        G = H // K
         pos = self.pos
-        c = self.cos.index_select(0, pos).view(1, 1, -1)
-        s = self.sin.index_select(0, pos).view(1, 1, -1)
-        mask = (self.ar[:bucket] > pos).view(1, 1, 1, bucket)
+        c = self.cos.index_select(0, pos).view(1, 1, hd)
+        s = self.sin.index_select(0, pos).view(1, 1, hd)
+        mask = (self.ar[:bucket] <= pos).view(1, 1, 1, bucket)
         x = self.emb.index_select(0, tokens)
         for l in range(cfg.layers):
             qkv = (self._norm(x) @ self.wqkv[l]).view(S, H + 2 * K, hd)
-            q = self._rope(qkv[:, :H], c, s)
-            k = self._rope(qkv[:, H:H + K], c, s)
-            v = qkv[:, H + K:]
-            self.kc[l].index_copy_(2, pos, k.unsqueeze(2))
-            self.vc[l].index_copy_(2, pos, v.unsqueeze(2))
-            kk, vv = self.kc[l][:, :, :bucket], self.vc[l][:, :, :bucket]
-            att = torch.matmul(q.view(S, K, G, hd), kk.transpose(-1, -2)).float() / math.sqrt(hd)
-            att = att.masked_fill(mask, float("-inf")).softmax(-1).to(self.dtype)
-            o = torch.matmul(att, vv).reshape(S, H * hd)
-            x = x + o @ self.wo[l]
+            qk = self._rope(qkv[:, :H + K], c, s)
+            self.kc[l].index_copy_(2, pos, qk[:, H:].unsqueeze(2))
+            self.vc[l].index_copy_(2, pos, qkv[:, H + K:].unsqueeze(2))
+            o = torch.nn.functional.scaled_dot_product_attention(
+                qk[:, :H].unsqueeze(2), self.kc[l][:, :, :bucket], self.vc[l][:, :, :bucket], attn_mask=mask,
+                enable_gqa=True)
+            x = x + o.reshape(S, H * hd) @ self.wo[l]
             h13 = self._norm(x) @ self.w13[l]
             x = x + (torch.nn.functional.silu(h13[:, :cfg.ffn]) * h13[:, cfg.ffn:]) @ self.w2[l]
         return (self._norm(x) @ self.head).float()
@@ -289,3 +290,71 @@ class LlamaCompressor:
         if c.tag and c.tag != self.tag:
             raise ValueError("container was written with a different predictor configuration")
         return sharding.decompress_sharded(blob, self.engine.decode_batch, self.model.device, self.group)
+
+
+# ------------------------------------------------------------------ the reference's own entry points
+from .arith_code import AC, ProbPredictor  # noqa: E402
+
+
+class Llama_AC(ProbPredictor):
+    """Drop-in for the reference's Llama_AC (llama_compress.py:14-61): a predictor around a llama_cpp.Llama-like
+    object -- anything with reset(), eval(tokens), n_ctx() and _scores[-1] (the fp32 logits row of the current
+    position, numpy or torch).  AC(Llama_AC(llm), 48).to_bin / .from_bin then code through the LQ32 kernels: the
+    row goes to the device once per token (logits_row) and lac_ac_encode_logits_f32 / lac_ac_decode_logits_f32 do
+    calc_dist + symbol_to_range / val_to_symbol + the coder step.  The tables are LQ32's, not the reference's
+    cumsum(clip(softmax * 2^60, 2)) (whose re-scaling wraps int64), so the bitstreams are not
+    interchangeable with the reference's; calc_dist() returns the LQ32 table in the reference's layout (inclusive
+    cumulative, total 2^32) for callers that look at it."""
+
+    def __init__(self, llm, maxtoks=2048):
+        super().__init__(0)
+        self.llm = llm
+        self.overlap = 2
+        self.reset()
+
+    def reset(self):                                       # :20-23
+        self.past = [BOS]
+        self.llm.reset()
+        self.llm.eval([BOS])
+        self.dcache = None
+
+    def logits_row(self) -> torch.Tensor:
+        row = self.llm._scores[-1]
+        if not isinstance(row, torch.Tensor):
+            row = torch.from_numpy(np.ascontiguousarray(row, dtype=np.float32))
+        return row.to(device="cuda", dtype=torch.float32).contiguous().view(-1)
+
+    def calc_dist(self):                                   # :24-30, LQ32 instead of the float cumsum
+        cum = coder.cdf_build(self.logits_row().view(1, -1))
+        self.dcache = coder.cdf_to_dist(cum)[0]
+        return self.dcache
+
+    @property
+    def minp(self):                                        # :43-45
+        d = self.dist
+        return int(min(int(d[0]), int(np.min(np.diff(d)))))
+
+    def accept(self, symbol):                              # :31-39
+        self.past.append(symbol)
+        if len(self.past) == self.llm.n_ctx():
+            self.past = self.past[self.llm.n_ctx() - self.llm.n_ctx() // self.overlap:]
+            self.llm.reset()
+            self.llm.eval(self.past)
+        else:
+            self.llm.eval([symbol])
+        return super().accept(symbol)
+
+    def copy(self):                                        # :40-41
+        return Llama_AC(self.llm)
+
+
+_llm = None
+
+
+def r(model_path="../../llama.cpp/models/llama-2-7b.ggmlv3.q5_1.bin", prec=48):
+    """llama_compress.py:4-10: AC(Llama_AC(llama_cpp.Llama(model_path, n_ctx=512)), prec)."""
+    import llama_cpp
+    global _llm
+    if _llm is None:
+        _llm = llama_cpp.Llama(model_path=model_path, n_ctx=512)
+    return AC(Llama_AC(_llm), prec)

@@ -340,11 +340,137 @@ def gen_ac_uniform(rng):
     print("ac_uniform:", len(names), "cases")
 
 
+# ---------------------------------------------------------------- call-by-call traces of the incremental APIs
+def _ragged(store, name, key, seqs, dtype):
+    flat = [x for q in seqs for x in q]
+    store[f"{name}/{key}"] = np.array(flat, dtype=dtype)
+    store[f"{name}/{key}_off"] = np.cumsum([0] + [len(q) for q in seqs]).astype(np.int64)
+
+
+def gen_api_traces(rng):
+    """What the reference returns call by call: A_to_bin.__call__(symbol) digit tuples (2s included), the state after
+    every call (l, h, emitted_bits, certain, info), flush digits; A_from_bin.__call__(bit) symbol tuples and state;
+    ACSampler's callback traffic (bits handed to compress_output per sample call, bits_per_token values; in expand
+    mode the bits pulled per call)."""
+    store, names = {}, []
+    cases = []
+    for prec, V, style in ((16, 3, "flat"), (16, 5, "skew"), (24, 17, "skew"), (32, 64, "skew"), (48, 64, "flat"),
+                           (48, 17, "big"), (32, 5, "big")):
+        if style == "flat":
+            pdf = [1] * V
+        elif style == "skew":
+            pdf = [int(rng.integers(1, 40)) for _ in range(V)]
+            pdf[int(rng.integers(0, V))] += 500
+        else:
+            pdf = [int(rng.integers(1, 1 << 30)) for _ in range(V)]
+        dist = list(np.cumsum(np.array(pdf, dtype=object)))
+        cases.append(("cdf", prec, V, dist))
+    for prec, n in ((16, 3), (24, 10), (48, 256)):
+        cases.append(("uniform", prec, n, None))
+    cases.append(("adaptive", 32, 16, None))
+    for kind, prec, V, dist in cases:
+        def make():
+            if kind == "cdf":
+                return ac.CDFPredictor(dist)
+            if kind == "uniform":
+                return ac.Predictor(V)
+            return AdaptiveCounts(V)
+        for n in (1, 9, 40):
+            syms = [int(x) for x in rng.integers(0, V, size=n)]
+            enc = ac.AC(make(), prec).to_bin
+            digits, states = [], []
+            for sy in syms:
+                digits.append([int(d) for d in enc(sy)])
+                states.append([enc.l, enc.h, enc.emitted_bits, int(enc.certain)])
+            infos = [0.0]  # info after the last symbol, before the flush
+            infos[0] = float(enc.info)
+            tee = float(enc.total_encoded_entropy)
+            digits.append([int(d) for d in enc(None)])
+            states.append([enc.l, enc.h, enc.emitted_bits, int(enc.certain)])
+            bits = [int(b) for b in ac.AC(make(), prec).to_bin.bits(syms, 1)]
+            dec = ac.AC(make(), prec).from_bin
+            outs, dstates, err = [], [], ""
+            try:
+                for b in bits:
+                    outs.append([int(x) for x in dec(b)])
+                    dstates.append([dec.l, dec.h, dec.lb, dec.hb])
+            except Exception as e:
+                err = type(e).__name__
+            name = f"t{len(names)}"
+            names.append(name)
+            pack_case(store, name, kind=kind, prec=prec, V=V, dist=np.array(dist if dist else [0], dtype=np.int64),
+                      syms=np.array(syms, dtype=np.int32), bits=np.array(bits, dtype=np.uint8),
+                      enc_states=np.array(states, dtype=np.int64), info=infos[0], total_encoded_entropy=tee,
+                      dec_states=np.array(dstates, dtype=np.int64).reshape(-1, 4), dec_err=err)
+            _ragged(store, name, "digits", digits, np.int32)
+            _ragged(store, name, "dec_out", outs, np.int32)
+    # ACSampler callback protocol
+    anames = []
+    for prec, V in ((16, 3), (32, 10), (48, 50), (48, 256)):
+        n = int(rng.integers(5, 40))
+        pdfs = [rng.dirichlet(np.ones(V) * 2.0) for _ in range(n)]
+        toks = [int(rng.choice(V, p=p)) for p in pdfs]
+        s = acs.ACSampler(prec)
+        cdfs = []
+        for p in pdfs:
+            q = np.array(p, dtype=np.float64)
+            q += s.get_lop_bias(q)
+            q *= s.region.one / np.sum(q)
+            cdfs.append(np.cumsum(q).astype(np.uint64))
+        out, per_call, bpt = [], [], []
+        s.compress_tokens = toks
+        s.compress_output = out.append
+        s.bits_per_token = bpt.append
+
+        def done(s=s):
+            s.on_compress_done = None
+            s.flush_compress()
+            s.compress_output = None
+            s.bits_per_token = None
+        s.on_compress_done = done
+        i = 0
+        while not s.compress_done:
+            before = len(out)
+            s.sample_scaled_cdf(cdfs[min(i, n - 1)])
+            per_call.append(len(out) - before)
+            i += 1
+        d = acs.ACSampler(prec)
+        pulled = [0]
+
+        def counting(bits):
+            for b in bits:
+                pulled[0] += 1
+                yield b
+        d.decompress_bits = counting(out)
+        dtoks, dpull, err = [], [], ""
+        try:
+            for i in range(n):
+                before = pulled[0]
+                dtoks.append(int(d.sample_scaled_cdf(cdfs[i])))
+                dpull.append(pulled[0] - before)
+        except Exception as e:
+            err = type(e).__name__
+        name = f"a{len(anames)}"
+        anames.append(name)
+        pack_case(store, name, prec=prec, cdf=np.stack(cdfs), toks=np.array(toks, dtype=np.int32),
+                  bits=np.array(out, dtype=np.uint8), per_call=np.array(per_call, dtype=np.int32),
+                  bits_per_token=np.array(bpt, dtype=np.float64), dec=np.array(dtoks, dtype=np.int32),
+                  dec_pulled=np.array(dpull, dtype=np.int32), dec_err=err)
+    store["names"] = np.array(names)
+    store["acs_names"] = np.array(anames)
+    np.savez_compressed(os.path.join(HERE, "api_traces.npz"), **store)
+    print("api_traces:", len(names), "coder cases,", len(anames), "sampler cases")
+
+
 if __name__ == "__main__":
-    rng = np.random.default_rng(20261018)
-    gen_ac_small(rng)
-    gen_ac_llama(rng)
-    gen_ac_adaptive()
-    gen_acs(rng)
-    gen_acs_64k()
-    gen_ac_uniform(np.random.default_rng(20261019))
+    which = sys.argv[1:]
+    if not which or "all" in which:
+        rng = np.random.default_rng(20261018)
+        gen_ac_small(rng)
+        gen_ac_llama(rng)
+        gen_ac_adaptive()
+        gen_acs(rng)
+        gen_acs_64k()
+        gen_ac_uniform(np.random.default_rng(20261019))
+    if not which or "all" in which or "api_traces" in which:
+        gen_api_traces(np.random.default_rng(20261020))
