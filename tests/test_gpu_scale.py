@@ -1,0 +1,153 @@
+"""GPU tests at the BASELINE.json shapes (run with -m gpu on a B200): level-2 parity measured on the product's
+actual bitstreams, state carry-over at full width, the 8192-stream x vocab-128256 decode-heavy shape.
+
+Sizes the oracle cannot walk in seconds are covered through size-independent properties (slices == one shot,
+encode -> decode round trip) plus an oracle check on a sample of the streams."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():  # collected on CPU boxes, deselected by -m "not gpu"
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from lac_b200 import _ffi, coder  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+
+def _oracle_stream(logits_s, syms_s, prec=48):
+    lo, hi = orc.lq32_lookup(logits_s, syms_s)
+    return orc.pack_bits(orc.ac_encode_pairs(lo, hi, prec=prec)).tobytes()
+
+
+# ------------------------------------------------------------------ level-2 parity, measured on the product
+@pytest.mark.parametrize("V,S,T", [(32000, 64, 16), (128256, 64, 16)])
+def test_compressed_size_within_a_tenth_of_a_percent_of_the_reference_tables(V, S, T):
+    """north_star level 2: 'given identical logits ... compressed size stays within 0.1 % of the reference'.
+    The GPU's ACTUAL bitstream lengths for >= 1024 logits rows, against the bit count of coding the same symbols
+    with the reference's own tables -- Llama_AC.calc_dist (llama_compress.py:24-30) -- under exact-integer
+    CDFPredictor semantics (arith_code.py:76-110, the oracle with wrap64 = 0), prec 48.
+
+    Logit scales 1 ... 30 per stream.  Where a row has a logit above ~88.7 the reference's np.exp overflows float32
+    (inf / nan tables, it cannot code such rows at all): those streams are counted, round-tripped on the GPU, and
+    left out of the size comparison.  (The reference as literally written does worse than both on every stream:
+    Llama_AC.fudged_dist wraps int64 -- DESIGN.md section 1 -- and codes at ~log2 V bits per token.)"""
+    rng = np.random.default_rng(V + 1)
+    scales = np.linspace(1.0, 30.0, S)
+    # streams alternate between two symbol populations: drawn from the model's own distribution (what a coder sees
+    # on text the model predicts -- the population the 0.1 % claim is about), and uniformly random ids (mostly symbols
+    # far rarer than 2^-32, where LQ32's floor of 2^-32 is CHEAPER than the reference's 2^-48 after re-scaling)
+    bits = {"model": [0, 0], "uniform": [0, 0]}
+    skipped = tokens = 0
+    for s0 in range(0, S, 8):   # 8 streams at a time keeps the int64 reference tables (8 V bytes per row) small
+        sc = scales[s0:s0 + 8]
+        n = len(sc)
+        logits = (rng.standard_normal((n, T, V)) * sc[:, None, None]).astype(np.float32)
+        syms = np.zeros((n, T), dtype=np.int32)
+        for i in range(n):
+            for t in range(T):
+                if i % 2 == 0:
+                    x = logits[i, t].astype(np.float64)
+                    p = np.exp(x - x.max())
+                    syms[i, t] = rng.choice(V, p=p / p.sum())
+                else:
+                    syms[i, t] = rng.integers(0, V)
+        dl = torch.from_numpy(logits).cuda()
+        enc = coder.StreamEncoder(n, capacity_bytes=T * 8 + 64)
+        enc.encode_logits(dl, torch.from_numpy(syms).cuda(), finish=True)
+        streams, nbits = enc.bitstreams()
+        assert np.array_equal(coder.StreamDecoder(streams).decode_logits(dl).cpu().numpy(), syms)
+        for i in range(n):
+            if float(logits[i].max()) > 88.0:
+                skipped += 1
+                continue
+            tables = np.stack([orc.ref_calc_dist(logits[i, t]) for t in range(T)])
+            ref = orc.ac_encode(tables, syms[i], prec=48, stop=1, kind="cdf", wrap64=False)
+            acc = bits["model" if i % 2 == 0 else "uniform"]
+            acc[0] += int(nbits[i])
+            acc[1] += len(ref)
+            tokens += T
+    assert tokens >= 0.4 * S * T and skipped > 0          # both kinds of rows are present
+    r_model = bits["model"][0] / bits["model"][1]
+    r_unif = bits["uniform"][0] / bits["uniform"][1]
+    print(f"V={V}: model-drawn symbols: GPU {bits['model'][0]} bits vs reference tables {bits['model'][1]} bits, ratio "
+          f"{r_model:.6f}; uniform symbols: {bits['uniform'][0]} vs {bits['uniform'][1]}, ratio {r_unif:.6f}; {tokens} tokens "
+          f"compared, {skipped} streams beyond the reference's float32 exp range")
+    assert abs(r_model - 1.0) <= 0.001, r_model      # within 0.1 % on in-distribution symbols
+    assert r_unif <= 1.001, r_unif                   # never more than 0.1 % larger
+
+
+# ------------------------------------------------------------------ configs[1] at full width
+def test_full_width_state_carry_1024_streams():
+    """1024 streams x vocab 32000 (configs[1]'s width): 48 tokens coded as 3 slices of 16 with the coder state
+    carried == the same 48 tokens in one call; the decoder walks the slices with its state carried; a sample of
+    streams is checked against the oracle."""
+    S, V, T, SL = 1024, 32000, 48, 16
+    g = torch.Generator(device="cuda").manual_seed(5)
+    logits = torch.randn((S, T, V), generator=g, device="cuda") * 3.0
+    probs = torch.softmax(logits.view(S * T, V), -1)
+    syms = torch.multinomial(probs, 1, generator=g).view(S, T).to(torch.int32)
+    del probs
+    one = coder.StreamEncoder(S, capacity_bytes=T * 8 + 64)
+    one.encode_logits(logits, syms, finish=True)
+    want, want_bits = one.bitstreams()
+    ws = coder.Workspace(S * SL, V)
+    sl = coder.StreamEncoder(S, capacity_bytes=T * 8 + 64)
+    for t0 in range(0, T, SL):
+        sl.encode_logits(logits[:, t0:t0 + SL].contiguous(), syms[:, t0:t0 + SL].contiguous(),
+                         finish=(t0 + SL >= T), ws=ws)
+    got, got_bits = sl.bitstreams()
+    assert got == want and np.array_equal(got_bits, want_bits)
+    dec = coder.StreamDecoder(want)
+    back = torch.cat([dec.decode_logits(logits[:, t0:t0 + SL].contiguous(), ws=ws) for t0 in range(0, T, SL)], dim=1)
+    assert torch.equal(back, syms)
+    hl, hs = logits[:3].cpu().numpy(), syms[:3].cpu().numpy()
+    for s in range(3):
+        assert want[s] == _oracle_stream(hl[s], hs[s])
+    # in-distribution symbols under N(0, 3^2) logits: about 8.8 bits per token
+    assert 8.0 < float(want_bits.sum()) / (S * T) < 9.6
+
+
+# ------------------------------------------------------------------ configs[4] shape
+def test_8192_streams_vocab_128256_token_steps():
+    """The decode-heavy shape: 8192 concurrent streams, vocab 128256, T = 1 per call (4.2 GB of logits per step):
+    three encode steps and three decode steps with carried state, lossless; a sample of streams against the
+    oracle; the decoder call's achieved bandwidth is printed."""
+    S, V, steps = 8192, 128256, 3
+    g = torch.Generator(device="cuda").manual_seed(6)
+    ws = coder.Workspace(S, V)
+    enc = coder.StreamEncoder(S, capacity_bytes=steps * 8 + 64)
+    logits = torch.empty((S, V), dtype=torch.float32, device="cuda")
+    syms, keep_l, keep_s = [], [], []
+    for t in range(steps):
+        g.manual_seed(100 + t)
+        logits.normal_(0.0, 3.0, generator=g)
+        sy = torch.randint(0, V, (S,), generator=g, device="cuda", dtype=torch.int32)
+        sy[:64] = torch.argmax(logits[:64], -1).to(torch.int32)       # some likely symbols among the uniform ones
+        enc.encode_step(logits, sy, ws=ws)
+        syms.append(sy.clone())
+        keep_l.append(logits[:2].cpu().numpy())
+        keep_s.append(sy[:2].cpu().numpy())
+    enc.finish()
+    streams, nbits = enc.bitstreams()
+    dec = coder.StreamDecoder(streams)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ms = []
+    for t in range(steps):
+        g.manual_seed(100 + t)
+        logits.normal_(0.0, 3.0, generator=g)
+        torch.randint(0, V, (S,), generator=g, device="cuda", dtype=torch.int32)   # keep the generator in step
+        ev[0].record()
+        out = dec.decode_step(logits, ws=ws)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms.append(ev[0].elapsed_time(ev[1]))
+        assert torch.equal(out, syms[t]), f"step {t}"
+    assert dec.status() == 0
+    for s in range(2):
+        lg = np.stack([keep_l[t][s] for t in range(steps)])
+        sy = np.array([keep_s[t][s] for t in range(steps)], dtype=np.int32)
+        assert streams[s] == _oracle_stream(lg, sy)
+    print(f"decode step, {S} streams x vocab {V}: {min(ms):.3f} ms = {S * V * 4 / min(ms) / 1e6:.0f} GB/s")
