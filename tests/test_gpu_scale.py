@@ -23,12 +23,21 @@ def _oracle_stream(logits_s, syms_s, prec=48):
 
 
 # ------------------------------------------------------------------ level-2 parity, measured on the product
-@pytest.mark.parametrize("V,S,T", [(32000, 64, 16), (128256, 64, 16)])
+def _entropy_coded(low, high, nbits, prec=48):
+    """A_to_bin.total_encoded_entropy (arith_code.py:221-226): bits emitted + the information still held in the
+    interval -- the size of the stream up to the +-2 bits of its termination."""
+    return float(nbits) + prec - float(np.log2(float(high - low + 1)))
+
+
+@pytest.mark.parametrize("V,S,T", [(32000, 64, 32), (128256, 64, 16)])
 def test_compressed_size_within_a_tenth_of_a_percent_of_the_reference_tables(V, S, T):
     """north_star level 2: 'given identical logits ... compressed size stays within 0.1 % of the reference'.
-    The GPU's ACTUAL bitstream lengths for >= 1024 logits rows, against the bit count of coding the same symbols
-    with the reference's own tables -- Llama_AC.calc_dist (llama_compress.py:24-30) -- under exact-integer
-    CDFPredictor semantics (arith_code.py:76-110, the oracle with wrap64 = 0), prec 48.
+    The size the GPU coder ACTUALLY produced for >= 1024 logits rows -- bits written plus the information held in
+    its final interval, read from the device coder state (the reference's own total_encoded_entropy) -- against the
+    same quantity from coding the same symbols with the reference's own tables, Llama_AC.calc_dist
+    (llama_compress.py:24-30), under exact-integer CDFPredictor semantics (arith_code.py:76-110, the oracle with
+    wrap64 = 0), prec 48.  The flushed byte streams are compared as well (they carry up to 2 bits of termination
+    per stream either way) and decoded back.
 
     Logit scales 1 ... 30 per stream.  Where a row has a logit above ~88.7 the reference's np.exp overflows float32
     (inf / nan tables, it cannot code such rows at all): those streams are counted, round-tripped on the GPU, and
@@ -39,8 +48,10 @@ def test_compressed_size_within_a_tenth_of_a_percent_of_the_reference_tables(V, 
     # streams alternate between two symbol populations: drawn from the model's own distribution (what a coder sees
     # on text the model predicts -- the population the 0.1 % claim is about), and uniformly random ids (mostly symbols
     # far rarer than 2^-32, where LQ32's floor of 2^-32 is CHEAPER than the reference's 2^-48 after re-scaling)
-    bits = {"model": [0, 0], "uniform": [0, 0]}
-    skipped = tokens = 0
+    size = {"model": [0.0, 0.0], "uniform": [0.0, 0.0]}      # information coded: GPU, reference tables
+    flushed = {"model": [0, 0], "uniform": [0, 0]}           # bits of the terminated streams
+    n_cmp = {"model": 0, "uniform": 0}
+    skipped = 0
     for s0 in range(0, S, 8):   # 8 streams at a time keeps the int64 reference tables (8 V bytes per row) small
         sc = scales[s0:s0 + 8]
         n = len(sc)
@@ -56,7 +67,9 @@ def test_compressed_size_within_a_tenth_of_a_percent_of_the_reference_tables(V, 
                     syms[i, t] = rng.integers(0, V)
         dl = torch.from_numpy(logits).cuda()
         enc = coder.StreamEncoder(n, capacity_bytes=T * 8 + 64)
-        enc.encode_logits(dl, torch.from_numpy(syms).cuda(), finish=True)
+        enc.encode_logits(dl, torch.from_numpy(syms).cuda(), finish=False)
+        st = enc.state.cpu().numpy().view(np.int64).reshape(n, 4)       # low, high, bits emitted, status
+        enc.finish()
         streams, nbits = enc.bitstreams()
         assert np.array_equal(coder.StreamDecoder(streams).decode_logits(dl).cpu().numpy(), syms)
         for i in range(n):
@@ -64,19 +77,24 @@ def test_compressed_size_within_a_tenth_of_a_percent_of_the_reference_tables(V, 
                 skipped += 1
                 continue
             tables = np.stack([orc.ref_calc_dist(logits[i, t]) for t in range(T)])
-            ref = orc.ac_encode(tables, syms[i], prec=48, stop=1, kind="cdf", wrap64=False)
-            acc = bits["model" if i % 2 == 0 else "uniform"]
-            acc[0] += int(nbits[i])
-            acc[1] += len(ref)
-            tokens += T
-    assert tokens >= 0.4 * S * T and skipped > 0          # both kinds of rows are present
-    r_model = bits["model"][0] / bits["model"][1]
-    r_unif = bits["uniform"][0] / bits["uniform"][1]
-    print(f"V={V}: model-drawn symbols: GPU {bits['model'][0]} bits vs reference tables {bits['model'][1]} bits, ratio "
-          f"{r_model:.6f}; uniform symbols: {bits['uniform'][0]} vs {bits['uniform'][1]}, ratio {r_unif:.6f}; {tokens} tokens "
-          f"compared, {skipped} streams beyond the reference's float32 exp range")
+            ref, rst = orc.ac_encode(tables, syms[i], prec=48, stop=1, kind="cdf", wrap64=False, return_state=True)
+            kind = "model" if i % 2 == 0 else "uniform"
+            size[kind][0] += _entropy_coded(int(st[i, 0]), int(st[i, 1]), int(st[i, 2]))
+            size[kind][1] += _entropy_coded(int(rst[0]), int(rst[1]), int(rst[2]))
+            flushed[kind][0] += int(nbits[i])
+            flushed[kind][1] += len(ref)
+            n_cmp[kind] += 1
+    assert n_cmp["model"] * T + n_cmp["uniform"] * T >= 0.4 * S * T and skipped > 0   # both kinds of rows are present
+    r_model = size["model"][0] / size["model"][1]
+    r_unif = size["uniform"][0] / size["uniform"][1]
+    print(f"V={V}: model-drawn symbols: GPU {size['model'][0]:.1f} bits vs reference tables {size['model'][1]:.1f} bits, "
+          f"ratio {r_model:.6f} (flushed streams {flushed['model'][0]} vs {flushed['model'][1]} bits); uniform symbols: "
+          f"{size['uniform'][0]:.1f} vs {size['uniform'][1]:.1f}, ratio {r_unif:.6f}; {n_cmp['model'] + n_cmp['uniform']} "
+          f"streams x {T} tokens compared, {skipped} streams beyond the reference's float32 exp range")
     assert abs(r_model - 1.0) <= 0.001, r_model      # within 0.1 % on in-distribution symbols
     assert r_unif <= 1.001, r_unif                   # never more than 0.1 % larger
+    for kind in ("model", "uniform"):                # the terminated streams: same, up to 2 bits per stream
+        assert flushed[kind][0] <= flushed[kind][1] * 1.001 + 2 * n_cmp[kind], kind
 
 
 # ------------------------------------------------------------------ configs[1] at full width
