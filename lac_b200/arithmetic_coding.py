@@ -17,7 +17,7 @@ reads the state back and hands the kernel's output to the callbacks:
   * compress: the stream bytes on the device are carry-resolved, which is what CarryBuffer does (:180-208); the
     bits not yet handed to compress_output are handed over whenever Region.definite holds after a token (the
     reference checks after every bit, so the same bits arrive in the same order, at most one token later);
-  * expand: (d_bits, d_bits_ulp), the window of code values the bits read so far allow (:96-106), is the bit
+  * expand: (d_bits, d_bits_ulp), the window of code values the bits read so far allow (:99-109), is the bit
     READER's state and is kept on the host; the device decodes the token at both ends of the window (two decoder
     states sharing the region) and another bit is pulled from decompress_bits while they disagree.
 
@@ -25,7 +25,7 @@ reads the state back and hands the kernel's output to the callbacks:
 reference's quantisation, not ours; the LLM path uses LQ32 on the GPU.
 
 Decoder semantics: the token returned is the one whose encoder interval contains the code
-value.  The reference's lookup (bisect_left with key=Region.map, :95) disagrees with its own encoder at interval
+value.  The reference's lookup (bisect_left with key=Region.map, :98) disagrees with its own encoder at interval
 boundaries and round-trips only part of its streams; the mirror decodes what the encoder coded.
 """
 from __future__ import annotations

@@ -195,7 +195,7 @@ class StreamEncoder:
 
     def acs_encode_tables(self, cdf: torch.Tensor, syms: torch.Tensor, ntok: Optional[torch.Tensor] = None,
                           finish=False):
-        """ACSampler semantics (arithmetic_coding.py:73-93): int64-carried uint64 inclusive tables.
+        """ACSampler semantics (arithmetic_coding.py:73-95): int64-carried uint64 inclusive tables.
         finish=True: the reference's flush_compress (bit-exact; tail tokens may be undecodable);
         finish="safe": A_to_bin-style termination, always decodable."""
         _need_cuda(cdf, "cdf", torch.int64)

@@ -31,43 +31,50 @@
 #include "ptx.cuh"
 #include "rowsum.cuh"
 
+#ifndef LAC_DEFAULT_TILE_WARPS
+#define LAC_DEFAULT_TILE_WARPS 32
+#endif
+
 namespace lac {
 
-constexpr int kThreads = 1024;
-constexpr int kWarps = kThreads / 32;
+constexpr int kMaxWarps = 32;
 
-// TMA chunks per tile.  Measured on B200 (profiles/microbench/tma_stream.cu): every cp.async.bulk costs
-// ~0.2 us of per-SM TMA time regardless of size, so 8 x 16 KB chunks cap at 4.7 TB/s while 2 x 64 KB
-// reach 7.2 TB/s with the same 128 KB in flight.
+// A tile is TW consecutive segments of a row (TW = 32: one part of the row, one CTA of 1024 threads per SM;
+// TW = 16 / 8: half / quarter parts, 2 / 4 CTAs of 512 / 256 threads per SM whose staging and compute phases
+// interleave).  It arrives as NCH TMA chunks.  Measured on B200 (profiles/microbench/tma_stream.cu): every
+// cp.async.bulk costs ~0.2 us of per-SM TMA time regardless of size, so 16 KB chunks cap at 4.7 TB/s while 32 and
+// 64 KB chunks reach 7.1 - 7.2 TB/s with the same 128 KB in flight per SM.
 constexpr int kMaxChunks = 8;
-template <int NCH>
+template <int NCH, int TW>
 struct Ring {
-    static constexpr int kWarpsPerChunk = kWarps / NCH;
+    static constexpr int kWarpsPerChunk = TW / NCH;
     static constexpr int kSlotGroups = kPerThread / 4 * 32 * kWarpsPerChunk + 1;  // float4 groups per slot
     static constexpr int kSlotBytes = kSlotGroups * 16;
     static constexpr int kRingBytes = NCH * kSlotBytes;
 };
 
-// Everything the pass needs to find tile `tau`: row rho = tau / parts (row (s, t) = (rho / T, rho % T) at
-// base + s * so + t * st), part p = tau % parts.  Lives in the kernel-parameter constant bank.
+// Everything the pass needs to find tile `tau`: row rho = tau / tpr (row (s, t) = (rho / T, rho % T) at
+// base + s * so + t * st), first segment (tau % tpr) * TW.  Lives in the kernel-parameter constant bank.
 struct SumParams {
     const float* base;
     int64_t so, st;
     uint32_t T, n_tiles;
     int V, G, parts;
     uint32_t inv_parts;  // ceil(2^31 / parts): floor(m / parts) = (m * inv_parts) >> 31 for m * parts < 2^31
+    uint32_t tpr;        // tiles per row = parts * 32 / TW
+    uint32_t inv_tpr;    // ceil(2^31 / tpr)
     int keep_l2;         // 0: stream with evict-first (the logits are read once); 1: leave them in L2 for a second pass
 };
 
 __shared__ uint64_t g_full[kMaxChunks];  // TMA chunk landed
-__shared__ int g_red[2][kWarps];         // per-warp maxima, written before the tile's barrier (see tile())
+__shared__ int g_red[2][kMaxWarps];      // per-warp maxima, written before the tile's barrier (see tile())
 extern __shared__ __align__(128) unsigned char g_ring[];
 
-template <int VEC, bool TMA, int NCH>
+template <int VEC, bool TMA, int NCH, int TW>
 struct TileEngine {
     static constexpr int IT = kPerThread / VEC;
-    static constexpr int kWarpsPerChunk = Ring<NCH>::kWarpsPerChunk;
-    static constexpr int kSlotBytes = Ring<NCH>::kSlotBytes;
+    static constexpr int kWarpsPerChunk = Ring<NCH, TW>::kWarpsPerChunk;
+    static constexpr int kSlotBytes = Ring<NCH, TW>::kSlotBytes;
 
     static __device__ __forceinline__ int warp() { return threadIdx.x >> 5; }
     static __device__ __forceinline__ int lane() { return threadIdx.x & 31; }
@@ -80,10 +87,11 @@ struct TileEngine {
         return (int)(((uint64_t)m * sp.inv_parts) >> 31);
     }
     static __device__ __forceinline__ uint32_t row_index(const SumParams& sp, uint32_t tau) {
-        return (uint32_t)(((uint64_t)tau * sp.inv_parts) >> 31);
+        return (uint32_t)(((uint64_t)tau * sp.inv_tpr) >> 31);
     }
-    static __device__ __forceinline__ uint32_t part_of(const SumParams& sp, uint32_t tau) {
-        return tau - row_index(sp, tau) * (uint32_t)sp.parts;
+    // first row-wide segment of tile tau
+    static __device__ __forceinline__ int seg0_of(const SumParams& sp, uint32_t tau) {
+        return (int)(tau - row_index(sp, tau) * sp.tpr) * TW;
     }
     static __device__ __forceinline__ const float* row_of(const SumParams& sp, uint32_t tau) {
         const uint32_t rho = row_index(sp, tau);
@@ -101,7 +109,7 @@ struct TileEngine {
     // chunk leader: arm the chunk's mbarrier and issue its bulk copy for tile tau
     static __device__ __forceinline__ void issue(const SumParams& sp, uint32_t tau) {
         if (TMA && leader()) {
-            const int gw0 = 32 * (int)part_of(sp, tau) + chunk() * kWarpsPerChunk;
+            const int gw0 = seg0_of(sp, tau) + chunk() * kWarpsPerChunk;
             const int g0 = seg(sp, gw0);
             const uint32_t nb = (uint32_t)(seg(sp, gw0 + kWarpsPerChunk) - g0) * 16u;
             if (nb) {
@@ -120,11 +128,11 @@ struct TileEngine {
                                                 uint64_t* __restrict__ summ) {
         float x[kPerThread];
         {
-            const int p = (int)part_of(sp, tau);
-            const int gw = 32 * p + warp();
+            const int s0 = seg0_of(sp, tau);
+            const int gw = s0 + warp();
             const int gb = seg(sp, gw), ge = seg(sp, gw + 1), ln = lane();
             if (TMA) {
-                const int gw0 = 32 * p + chunk() * kWarpsPerChunk;
+                const int gw0 = s0 + chunk() * kWarpsPerChunk;
                 const int c0 = seg(sp, gw0);
                 if (seg(sp, gw0 + kWarpsPerChunk) > c0) mbar_wait(&g_full[chunk()], it & 1);
                 const unsigned char* sl = slot() + (size_t)(gb + ln - c0) * 16;
@@ -209,14 +217,14 @@ struct TileEngine {
             lane_sum += (q0 + q1) + (q2 + q3);
         }
         const uint64_t ws = warp_sum48(lane_sum);
-        if (lane() == 0) summ[(uint64_t)tau * 32 + warp()] = lq::pack_word(ws, code);
+        if (lane() == 0) summ[(uint64_t)tau * TW + warp()] = lq::pack_word(ws, code);
     }
 };
 
-template <int VEC, bool TMA, int NCH>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int VEC, bool TMA, int NCH, int TW>
+__global__ void __launch_bounds__(32 * TW, 32 / TW)
 summary_kernel(const __grid_constant__ SumParams sp, uint64_t* __restrict__ summ) {
-    using Eng = TileEngine<VEC, TMA, NCH>;
+    using Eng = TileEngine<VEC, TMA, NCH, TW>;
     if (TMA) Eng::setup();
     uint32_t tau = blockIdx.x;
     if (tau < sp.n_tiles) Eng::issue(sp, tau);
@@ -239,7 +247,7 @@ pair_kernel(const float* __restrict__ logits, int64_t rows, int64_t T, int64_t s
     if (sym < 0 || sym >= V) {
         if (lane == 0) {
             // sentinel the coder turns into LAC_ST_SYMBOL on the stream (the reference raises "unknown symbol",
-            // arith_code.py:104-105); never a silent no-op
+            // arith_code.py:100-101); never a silent no-op
             *reinterpret_cast<uint2*>(pairs + 2 * r) = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
             if (status) atomicOr(status + r, LAC_ST_SYMBOL);
         }
@@ -324,20 +332,29 @@ int path_for(const float* p, int V, int64_t s0, int64_t s1, int* parts) {
     return (nch == 2 || nch == 8) ? nch : 4;  // 4 x 32 KB: 0.7 % faster than 2 x 64 KB with one barrier per tile
 }
 
-template <typename K>
-static cudaError_t launch_ring(K kernel, int ring_bytes, const SumParams& sp, uint64_t* summ, cudaStream_t st) {
+template <int TW, typename K>
+static cudaError_t launch_ring(K kernel, int ring_bytes, SumParams sp, uint64_t* summ, cudaStream_t st) {
+    sp.tpr = (uint32_t)(sp.parts * (32 / TW));
+    sp.inv_tpr = (uint32_t)(((1ull << 31) + sp.tpr - 1) / sp.tpr);
+    sp.n_tiles *= (uint32_t)(32 / TW);
     if (ring_bytes > 0) {
         const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes);
         if (e != cudaSuccess) return e;
     }
-    const int sms = sm_count();
-    const unsigned grid = sp.n_tiles < (uint32_t)sms ? sp.n_tiles : (unsigned)sms;
-    kernel<<<grid, kThreads, ring_bytes, st>>>(sp, summ);
+    const uint32_t slots = (uint32_t)sm_count() * (32 / TW);
+    const unsigned grid = sp.n_tiles < slots ? sp.n_tiles : slots;
+    kernel<<<grid, 32 * TW, ring_bytes, st>>>(sp, summ);
     return cudaGetLastError();
 }
 
+// Warps per tile / CTA: 32 (one CTA per SM), 16 or 8 (2 / 4 CTAs per SM).  LAC_TILE_WARPS is a measurement switch.
+static int tile_warps() {
+    static const int tw = getenv("LAC_TILE_WARPS") ? atoi(getenv("LAC_TILE_WARPS")) : LAC_DEFAULT_TILE_WARPS;
+    return (tw == 8 || tw == 16) ? tw : 32;
+}
+
 // Row summaries of rows (s, t), s < n_outer, t < T, at base + s * so + t * st; summary of row (s, t) at
-// summ + (s * T + t) * 32 * parts.  n_outer * T * parts must stay below 2^28 (summ_rows_for sees to it).
+// summ + (s * T + t) * 32 * parts.  n_outer * T * parts must stay below 2^26 (summ_rows_for sees to it).
 cudaError_t launch_summary(const float* base, int64_t n_outer, int64_t T, int64_t so, int64_t st_, int V, int parts,
                            int path, int keep_l2, uint64_t* summ, cudaStream_t st) {
     SumParams sp;
@@ -345,29 +362,34 @@ cudaError_t launch_summary(const float* base, int64_t n_outer, int64_t T, int64_
     sp.so = so;
     sp.st = st_;
     sp.T = (uint32_t)T;
-    sp.n_tiles = (uint32_t)(n_outer * T * parts);
+    sp.n_tiles = (uint32_t)(n_outer * T * parts);  // in parts; launch_ring scales it to tiles of TW warps
     sp.V = V;
     sp.G = lq::groups_of(V);
     sp.parts = parts;
     sp.inv_parts = (uint32_t)(((1ull << 31) + parts - 1) / parts);
+    sp.tpr = sp.inv_tpr = 0;
     sp.keep_l2 = keep_l2;
     if (sp.n_tiles == 0) return cudaSuccess;
+    const int tw = tile_warps();
+    // chunks of 8 warps (32 KB) unless LAC_TMA_CHUNKS asks otherwise (TW = 32 only)
+    if (path >= 2 && tw == 16) return launch_ring<16>(summary_kernel<4, true, 2, 16>, Ring<2, 16>::kRingBytes, sp, summ, st);
+    if (path >= 2 && tw == 8) return launch_ring<8>(summary_kernel<4, true, 1, 8>, Ring<1, 8>::kRingBytes, sp, summ, st);
     switch (path) {
-        case 2: return launch_ring(summary_kernel<4, true, 2>, Ring<2>::kRingBytes, sp, summ, st);
-        case 4: return launch_ring(summary_kernel<4, true, 4>, Ring<4>::kRingBytes, sp, summ, st);
-        case 8: return launch_ring(summary_kernel<4, true, 8>, Ring<8>::kRingBytes, sp, summ, st);
-        case 1: return launch_ring(summary_kernel<4, false, 4>, 0, sp, summ, st);
-        case 0: return launch_ring(summary_kernel<1, false, 4>, 0, sp, summ, st);
+        case 2: return launch_ring<32>(summary_kernel<4, true, 2, 32>, Ring<2, 32>::kRingBytes, sp, summ, st);
+        case 4: return launch_ring<32>(summary_kernel<4, true, 4, 32>, Ring<4, 32>::kRingBytes, sp, summ, st);
+        case 8: return launch_ring<32>(summary_kernel<4, true, 8, 32>, Ring<8, 32>::kRingBytes, sp, summ, st);
+        case 1: return launch_ring<32>(summary_kernel<4, false, 4, 32>, 0, sp, summ, st);
+        case 0: return launch_ring<32>(summary_kernel<1, false, 4, 32>, 0, sp, summ, st);
         default: return cudaErrorInvalidValue;
     }
 }
 
 // Rows of summary a launch may cover: the scratch budget (LAC_SUMMARY_BYTES: test switch, forces many small
-// chunks) and the tile index (the mul-shift division by `parts` is exact below 2^28 tiles).
+// chunks) and the tile index (the mul-shift division by the tiles per row is exact below 2^28 tiles).
 int64_t summ_chunk_rows(int parts) {
     static const int64_t budget = getenv("LAC_SUMMARY_BYTES") ? atoll(getenv("LAC_SUMMARY_BYTES")) : (64ll << 20);
     int64_t rows = budget / (32 * parts * 8 + 8);
-    const int64_t lim = ((1ll << 28) - 1) / parts;
+    const int64_t lim = ((1ll << 26) - 1) / (parts * 4);  // tiles per row <= 4 * parts
     if (rows > lim) rows = lim;
     return rows < 1 ? 1 : rows;
 }

@@ -10,7 +10,7 @@
 // token are produced at once: after k doublings l_k = (l_0 mod 2^(P-k)) * 2^k and the bits
 // are E = floor(l_0 / 2^(P-k)), which may carry (E >= 2^k) into bits already written, or
 // borrow (E < 0, flush only).  BitWriter resolves that exactly like A_to_bin.encode's
-// r = (r << 1) + v (arith_code.py:208-215) / CarryBuffer.add (arithmetic_coding.py:197-201).
+// r = (r << 1) + v (arith_code.py:212-219) / CarryBuffer.add (arithmetic_coding.py:198-202).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -76,7 +76,7 @@ struct BitWriter {
             append_small(E, k);
         }
     }
-    // store the partial byte zero-padded (group_bits' tail, arith_code.py:354-357); the bits
+    // store the partial byte zero-padded (group_bits' tail, arith_code.py:343-347); the bits
     // stay accounted in nbits so a later open() resumes mid-byte.
     __device__ void close() {
         if (nacc && !(status & LAC_ST_CAP)) {
@@ -174,7 +174,7 @@ struct StagedWriter {
             append_small(E, k);
         }
     }
-    // the partial byte, zero-padded (group_bits' tail, arith_code.py:345-348), goes behind the staged bytes; it stays
+    // the partial byte, zero-padded (group_bits' tail, arith_code.py:343-347), goes behind the staged bytes; it stays
     // accounted in nbits only, so a later open() resumes mid-byte
     __device__ void close() {
         if (nacc && !(status & LAC_ST_CAP)) {
@@ -191,7 +191,7 @@ struct StagedWriter {
 
 // ---------------------------------------------------------------- bit input
 // k bits starting at bit `pos` of data[0..nbytes), MSB first, zeros past the end
-// (A_from_bin sees no more bits; ACSampler substitutes 0, arithmetic_coding.py:103-106).
+// (A_from_bin sees no more bits; ACSampler substitutes 0, arithmetic_coding.py:102-107).
 __device__ __forceinline__ uint64_t read_bits(const uint8_t* data, uint64_t nbytes, uint64_t pos, int k) {
     if (k <= 0) return 0;
     uint64_t first = pos >> 3, last = (pos + (uint64_t)k - 1) >> 3;
@@ -202,7 +202,7 @@ __device__ __forceinline__ uint64_t read_bits(const uint8_t* data, uint64_t nbyt
 }
 
 // ---------------------------------------------------------------- renormalisation
-// Number of doublings the reference loop performs for a width `span` (arith_code.py:167-171
+// Number of doublings the reference loop performs for a width `span` (arith_code.py:176-180
 // `(h-l) < decision`; arithmetic_coding.py:170 `span*2 <= one`).
 __device__ __forceinline__ int renorm_count(uint64_t span, int P) {
     if (span > (1ull << (P - 1))) return 0;
@@ -221,14 +221,14 @@ __device__ __forceinline__ int64_t renorm_apply(int64_t& l, int64_t& h, int P, i
 }
 
 // ---------------------------------------------------------------- A_to_bin pieces
-// ceil(c * w / 2^32) for c <= 2^32, w <= 2^62: symbol_to_range (arith_code.py:110-113) on the
+// ceil(c * w / 2^32) for c <= 2^32, w <= 2^62: symbol_to_range (arith_code.py:105-109) on the
 // fixed total d = 2^32.
 __device__ __forceinline__ uint64_t scale32_ceil(uint64_t c, uint64_t w) {
     u128 p = (u128)c * w + 0xFFFFFFFFull;
     return (uint64_t)(p >> 32);
 }
 
-// receive_symbol (arith_code.py:160-166) with (lo, hi) on total 2^32; hi == 0 means 2^32.
+// receive_symbol (arith_code.py:169-175) with (lo, hi) on total 2^32; hi == 0 means 2^32.
 __device__ __forceinline__ void ac_narrow32(int64_t& l, int64_t& h, uint32_t lo, uint32_t hi) {
     uint64_t w = (uint64_t)(h - l + 1);
     uint64_t r0 = scale32_ceil(lo, w);
@@ -243,7 +243,7 @@ __device__ __forceinline__ int64_t region_overlap(int64_t a, int64_t b, int64_t 
     return v > 0 ? v : 0;
 }
 
-// A_to_bin.flush (arith_code.py:185-194), literal: at most P + 2 iterations.
+// A_to_bin.flush (arith_code.py:193-202), literal: at most P + 2 iterations.
 template <class Writer>
 __device__ inline void ac_flush(int64_t& l, int64_t& h, int P, Writer& bw) {
     const int64_t denom = 1ll << P, decision = 1ll << (P - 1);

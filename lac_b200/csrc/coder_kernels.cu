@@ -80,7 +80,7 @@ __global__ void encode_pairs_kernel(const uint2* __restrict__ pairs, int64_t n_s
             if (t0 + j < Ts && !bad) {
                 if (pr[j].y != 0 && pr[j].y <= pr[j].x) {
                     // the lookup's sentinel for a symbol outside [0, V) (the reference raises "unknown symbol",
-                    // arith_code.py:104-105), or a zero-width symbol (the reference would never terminate)
+                    // arith_code.py:100-101), or a zero-width symbol (the reference would never terminate)
                     bw.status |= (pr[j].x == 0xFFFFFFFFu && pr[j].y == 0xFFFFFFFFu) ? LAC_ST_SYMBOL : LAC_ST_TABLE;
                     bad = true;
                 } else if (bw.status & LAC_ST_CAP) {
@@ -220,7 +220,7 @@ encode_fused_kernel(const __grid_constant__ EncParams ep) {
     }
 }
 
-// ------------------------------------------------------------------ uniform Predictor(n) (arith_code.py:63-74)
+// ------------------------------------------------------------------ uniform Predictor(n) (arith_code.py:64-74)
 // The reference's base class maps symbol s of n to [floor(s w / n), floor((s + 1) w / n)) -- floor, not the ceil of
 // CDFPredictor.  AC() without arguments is AC(Predictor(3), 16).  One thread per stream.
 __global__ void uniform_encode_kernel(const int32_t* __restrict__ syms, int64_t n_streams, int64_t T, int64_t sym_stride,
@@ -240,13 +240,13 @@ __global__ void uniform_encode_kernel(const int32_t* __restrict__ syms, int64_t 
             break;
         }
         const u128 w = (u128)(uint64_t)(h - l + 1);
-        const int64_t r0 = (int64_t)(((u128)(uint32_t)sym * w) / (uint32_t)nsym);          // symbol_to_range :68-69
+        const int64_t r0 = (int64_t)(((u128)(uint32_t)sym * w) / (uint32_t)nsym);          // symbol_to_range :69-70
         const int64_t r1 = (int64_t)((((u128)(uint32_t)sym + 1) * w) / (uint32_t)nsym);
         if (r1 <= r0) {  // zero-width symbol (w < n): the reference would never terminate
             bw.status |= LAC_ST_TABLE;
             break;
         }
-        h = l + r1 - 1;  // receive_symbol :160-166
+        h = l + r1 - 1;  // receive_symbol :169-175
         l += r0;
         int k = coder::renorm_count((uint64_t)(h - l + 1), P);
         int64_t E = coder::renorm_apply(l, h, P, k);
@@ -360,7 +360,7 @@ __device__ inline void fudged_three(const TableCtx& c, int a, int64_t w, int64_t
     p_last = (c.V - 1) + (m_all > 1 ? m_all : 1);
 }
 
-// symbol_to_range (arith_code.py:102-114): offsets r0, r1 inside a width-w interval.
+// symbol_to_range (arith_code.py:98-110): offsets r0, r1 inside a width-w interval.
 __device__ inline bool table_range(const TableCtx& c, int sym, int64_t w, int lane, int64_t& r0, int64_t& r1) {
     const int64_t last = c.tbl[c.V - 1];
     int64_t ld, hd, d;
@@ -377,7 +377,7 @@ __device__ inline bool table_range(const TableCtx& c, int sym, int64_t w, int la
     return r1 > r0;
 }
 
-// val_to_symbol (arith_code.py:94-101): bisect_right(fudged_dist(w), (x * dist[-1]) // w).
+// val_to_symbol (arith_code.py:94-97): bisect_right(fudged_dist(w), (x * dist[-1]) // w).
 __device__ inline int table_symbol(const TableCtx& c, int64_t x, int64_t w, int lane) {
     const int64_t last = c.tbl[c.V - 1];
     int64_t cnt = 0;
@@ -532,7 +532,7 @@ __global__ void acs_tables_encode_kernel(const uint64_t* __restrict__ cdf, int V
             break;
         }
         const uint64_t* c = cdf + s * ss + t * ts;
-        // sample_scaled_cdf compress path, arithmetic_coding.py:83-87
+        // sample_scaled_cdf compress path, arithmetic_coding.py:85-87
         uint64_t cl = tok ? c[tok - 1] : 0, ch = c[tok], den = c[V - 1];
         if (den == 0 || ch <= cl) {
             bw.status |= LAC_ST_TABLE;
@@ -548,7 +548,7 @@ __global__ void acs_tables_encode_kernel(const uint64_t* __restrict__ cdf, int V
         if (bw.status & LAC_ST_CAP) break;
     }
     if (finish == 1 && !(bw.status & (LAC_ST_TABLE | LAC_ST_SYMBOL | LAC_ST_CAP))) {
-        // flush_compress, arithmetic_coding.py:52-58: step(1, 2, 3), drain the carry buffer, reset.
+        // flush_compress, arithmetic_coding.py:50-56: step(1, 2, 3), drain the carry buffer, reset.
         // Bit-exact with the reference, but the bits do not pin the final region (DESIGN.md
         // section 6): the last tokens may be undecodable by ANY decoder.
         coder::acs_narrow(low, high, 1, 2, 3);
@@ -558,7 +558,7 @@ __global__ void acs_tables_encode_kernel(const uint64_t* __restrict__ cdf, int V
         high = (1ll << P) - 1;
     } else if (finish == 2 && !(bw.status & (LAC_ST_TABLE | LAC_ST_SYMBOL | LAC_ST_CAP))) {
         // safe termination: shortest bit string whose every continuation stays inside [low, high]
-        // (A_to_bin.flush, arith_code.py:185-194) -- always decodable
+        // (A_to_bin.flush, arith_code.py:193-202) -- always decodable
         coder::ac_flush(low, high, P, bw);
     }
     bw.close();

@@ -197,7 +197,7 @@ decode_serial_kernel(const __grid_constant__ SerialParams rp, int V, const uint6
         sym = __shfl_sync(0xffffffffu, sym, src);
         lo = __shfl_sync(0xffffffffu, lo, src);
         hi = __shfl_sync(0xffffffffu, hi, src);
-        // ---- A_from_bin.emit_symbol + emit_bit loop (arith_code.py:272-298), the same in every lane
+        // ---- A_from_bin.emit_symbol + emit_bit loop (arith_code.py:274-291), the same in every lane
         int64_t nl = low, nh = high;
         coder::ac_narrow32(nl, nh, lo, hi);
         const int64_t off = value - nl;  // the value stays inside [nl, nh]

@@ -30,7 +30,7 @@
 //   s    = bitlen(Q) - 1,  Qn = Q normalised to [2^31, 2^32),  R = floor(((2^32 - V) << 31) / (Qn + 1))
 //   cum_i = ((C_i * R) >> s) + i,  cum_V = 2^32     => every frequency >= 1
 //
-// Replaces the reference's float table builders (llama_compress.py:24-30, arithmetic_coding.py:59-64); the
+// Replaces the reference's float table builders (llama_compress.py:24-30, arithmetic_coding.py:57-62); the
 // quantisation differs from theirs by design, bound in DESIGN.md section 3.
 #pragma once
 #include <cstdint>

@@ -1,6 +1,6 @@
 // rowsum.cuh -- what the second passes do with a row summary (lq32.cuh): one warp turns the NW = 32 * CL summary
 // words of a row into the row reference, the aligned segment weights, their prefixes and the row total, and
-// evaluates symbol_to_range (arith_code.py:102-114) for one symbol by re-reading only that symbol's segment
+// evaluates symbol_to_range (arith_code.py:98-110) for one symbol by re-reading only that symbol's segment
 // (<= 4 KB).  q is a function of (x, segment reference) only, so what is recomputed here is bit-identical to pass 1.
 #pragma once
 #include <cstdint>

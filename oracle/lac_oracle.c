@@ -32,12 +32,12 @@ typedef unsigned __int128 u128;
 #define ORC_OK 0
 #define ORC_E_ARG (-1)
 #define ORC_E_CAP (-2)      /* output buffer too small */
-#define ORC_E_SYMBOL (-3)   /* AssertionError("unknown symbol") arith_code.py:105 */
-#define ORC_E_RANGE (-4)    /* AssertionError("predictor range does not correspond to val") arith_code.py:283 */
+#define ORC_E_SYMBOL (-3)   /* AssertionError("unknown symbol") arith_code.py:100-101 */
+#define ORC_E_RANGE (-4)    /* AssertionError("predictor range does not correspond to val") arith_code.py:277-278 */
 #define ORC_E_CARRY (-5)    /* carry out of the first bit / negative bit: cannot happen for valid input */
-#define ORC_E_EMPTY (-6)    /* max() of empty range in A_from_bin.flush, arith_code.py:324 */
-#define ORC_E_ZERODIV (-7)  /* ZeroDivisionError in A_from_bin.flush key, arith_code.py:319 */
-#define ORC_E_INDEX (-8)    /* IndexError: ACSampler lookup ran off the cdf, arithmetic_coding.py:108 */
+#define ORC_E_EMPTY (-6)    /* max() of empty range in A_from_bin.flush, arith_code.py:312 */
+#define ORC_E_ZERODIV (-7)  /* ZeroDivisionError in A_from_bin.flush key, arith_code.py:305-307 */
+#define ORC_E_INDEX (-8)    /* IndexError: ACSampler lookup ran off the cdf, arithmetic_coding.py:114-115 */
 
 /* Python floor division for b > 0. */
 static inline i128 fdiv(i128 a, i128 b) {
@@ -45,20 +45,20 @@ static inline i128 fdiv(i128 a, i128 b) {
     if ((a % b != 0) && ((a < 0) != (b < 0))) q -= 1;
     return q;
 }
-/* Python -(-(a)//b): ceil for b > 0.  arith_code.py:111,113 */
+/* Python -(-(a)//b): ceil for b > 0.  arith_code.py:107,109 */
 static inline i128 cdiv(i128 a, i128 b) { return -fdiv(-a, b); }
 static inline i128 imin(i128 a, i128 b) { return a < b ? a : b; }
 static inline i128 imax(i128 a, i128 b) { return a > b ? a : b; }
 
-/* region_overlap, arith_code.py:58-60: inclusive [a,b] with inclusive [c,d]. */
+/* region_overlap, arith_code.py:59-61: inclusive [a,b] with inclusive [c,d]. */
 static inline i128 region_overlap(i128 a, i128 b, i128 c, i128 d) {
     return imax(0, imin(d, b) - imax(a, c) + 1);
 }
 
 /* ------------------------------------------------------------------ */
 /* Bit sink with carry resolution.  Restates what A_to_bin.encode       */
-/* (arith_code.py:194-201: r = (r<<1) + v) and A_to_bin.bits            */
-/* (arith_code.py:214-231) / CarryBuffer (arithmetic_coding.py:186-196) */
+/* (arith_code.py:212-219: r = (r<<1) + v) and A_to_bin.bits            */
+/* (arith_code.py:230-246) / CarryBuffer (arithmetic_coding.py:198-208) */
 /* compute: the binary expansion of sum_i v_i 2^-i, v_i small signed ints. */
 /* ------------------------------------------------------------------ */
 typedef struct {
@@ -68,7 +68,7 @@ typedef struct {
 } bitsink;
 
 static void sink_push(bitsink *s, i128 v) {
-    /* v may be negative: A_to_bin.flush (arith_code.py:185-194) emits floor(l/decision)
+    /* v may be negative: A_to_bin.flush (arith_code.py:193-202) emits floor(l/decision)
      * with l < 0, and encode()'s r = (r<<1) + v absorbs it as a borrow. */
     if (s->err) return;
     if (s->n >= s->cap) { s->err = ORC_E_CAP; return; }
@@ -85,8 +85,8 @@ static void sink_push(bitsink *s, i128 v) {
     s->n++;
 }
 
-/* group_bits (arith_code.py:347-358) == packbits + packbits.flush
- * (arithmetic_coding.py:200-214): MSB first, zero-pad the last byte. */
+/* group_bits (arith_code.py:336-347) == packbits + packbits.flush
+ * (arithmetic_coding.py:212-225): MSB first, zero-pad the last byte. */
 int64_t orc_pack_bits(const uint8_t *bits, int64_t nbits, uint8_t *out) {
     int64_t nb = (nbits + 7) / 8;
     memset(out, 0, (size_t)nb);
@@ -94,14 +94,14 @@ int64_t orc_pack_bits(const uint8_t *bits, int64_t nbits, uint8_t *out) {
         if (bits[i]) out[i >> 3] |= (uint8_t)(0x80u >> (i & 7));
     return nb;
 }
-/* ungroup_bits (arith_code.py:359-362) == unpackbits (arithmetic_coding.py:216-219). */
+/* ungroup_bits (arith_code.py:348-351) == unpackbits (arithmetic_coding.py:227-230). */
 void orc_unpack_bits(const uint8_t *bytes, int64_t nbytes, uint8_t *bits) {
     for (int64_t i = 0; i < nbytes; i++)
         for (int b = 0; b < 8; b++) bits[i * 8 + b] = (bytes[i] >> (7 - b)) & 1;
 }
 
 /* ------------------------------------------------------------------ */
-/* CDFPredictor (arith_code.py:75-114)                                  */
+/* CDFPredictor (arith_code.py:76-110)                                  */
 /* ------------------------------------------------------------------ */
 /* fudged_dist, arith_code.py:83-93.  Returns the table to use (dist or scratch). */
 /* wrap64: Llama_AC keeps dist as a numpy int64 array (llama_compress.py:29), so the
@@ -124,7 +124,7 @@ static const int64_t *fudged_dist(const int64_t *dist, int V, i128 minp, i128 de
     }
     return scratch;
 }
-/* CDFPredictor.minp, arith_code.py:78: min positive pdf entry (0 if none: the
+/* CDFPredictor.minp, arith_code.py:79: min positive pdf entry (0 if none: the
  * reference would raise ValueError; callers never pass such a table). */
 int64_t orc_cdf_minp(const int64_t *dist, int V) {
     int64_t best = 0, prev = 0;
@@ -144,8 +144,8 @@ int64_t orc_llama_minp(const int64_t *dist, int V) {
     }
     return best;
 }
-/* symbol_to_range, arith_code.py:102-114 (same body as llama_compress.py:49-61). */
-/* tbl == NULL: the uniform base class Predictor(V), arith_code.py:63-74 (floor-mapped). */
+/* symbol_to_range, arith_code.py:98-110 (same body as llama_compress.py:49-61). */
+/* tbl == NULL: the uniform base class Predictor(V), arith_code.py:64-74 (floor-mapped). */
 static int symbol_to_range(const int64_t *tbl, int V, int64_t s, i128 denom, i128 *r0, i128 *r1) {
     if (!tbl) {                                   /* Predictor.symbol_to_range :68-69: no bound on s (the */
         *r0 = fdiv((i128)s * denom, V);           /* decoder's flush() probes symbols past n - 1)          */
@@ -160,7 +160,7 @@ static int symbol_to_range(const int64_t *tbl, int V, int64_t s, i128 denom, i12
     *r1 = cdiv(hd * denom, d);
     return ORC_OK;
 }
-/* val_to_symbol, arith_code.py:94-101: bisect_right(dist, (v*dist[-1])//denom). */
+/* val_to_symbol, arith_code.py:94-97: bisect_right(dist, (v*dist[-1])//denom). */
 static int64_t val_to_symbol(const int64_t *tbl, int V, i128 v, i128 denom) {
     if (!tbl) return (int64_t)fdiv(v * (i128)V, denom);   /* Predictor.val_to_symbol :66-67 */
     i128 target = fdiv(v * (i128)tbl[V - 1], denom);
@@ -181,14 +181,14 @@ static inline const int64_t *table_at(const int64_t *dist, int64_t stride, int64
 }
 
 /* ------------------------------------------------------------------ */
-/* A_to_bin (arith_code.py:147-231)                                     */
+/* A_to_bin (arith_code.py:156-246)                                     */
 /* ------------------------------------------------------------------ */
 /*
  * dist     inclusive cumulative table(s) (CDFPredictor.dist), V entries each
  * stride   elements between consecutive positions' tables, 0 => one shared table
  * ntab     number of tables when stride != 0
  * minp     predictor.minp per table (1 entry when shared)
- * stop     run(..., stop): call flush() at the end (arith_code.py:187-191)
+ * stop     run(..., stop): call flush() at the end (arith_code.py:207-211)
  * bits     carry-resolved bit string == list(A_to_bin.bits(symbols, stop))
  *          == binary digits of A_to_bin.encode(symbols, stop)
  * state_out (optional, 3 x int64): l, h, emitted_bits before flush.
@@ -198,12 +198,12 @@ int orc_ac_encode(int prec, const int64_t *dist, int64_t stride, int64_t ntab, c
                   int64_t *nbits, int64_t *state_out, int wrap64) {
     if (prec < 2 || prec > 62 || V < 1) return ORC_E_ARG;
     const i128 denom = (i128)1 << prec, decision = (i128)1 << (prec - 1);
-    i128 l = 0, h = denom - 1;                                   /* :151-152 */
+    i128 l = 0, h = denom - 1;                                   /* :161-162 */
     int64_t *scratch = (int64_t *)malloc(sizeof(int64_t) * (size_t)V);
     bitsink sk = {bits, 0, cap, 0};
     int rc = ORC_OK;
     for (int64_t t = 0; t < n && !sk.err; t++) {
-        /* receive_symbol :160-166 */
+        /* receive_symbol :169-175 */
         i128 w = h - l + 1, mp, r0, r1;
         const int64_t *tbl = NULL;
         if (dist) {
@@ -216,7 +216,7 @@ int orc_ac_encode(int prec, const int64_t *dist, int64_t stride, int64_t ntab, c
         if (r1 <= r0) { rc = ORC_E_ZERODIV; break; }   /* zero-width symbol: the reference loops forever */
         h = l + r1 - 1;
         l += r0;
-        /* step :179-184 / decide_bit :167-171 / emit_bit :172-178 */
+        /* step :187-192 / decide_bit :176-180 / emit_bit :181-186 */
         while ((h - l) < decision) {
             i128 b = fdiv(l, decision);
             l = l * 2 - b * denom;
@@ -227,7 +227,7 @@ int orc_ac_encode(int prec, const int64_t *dist, int64_t stride, int64_t ntab, c
     }
     if (state_out) { state_out[0] = (int64_t)l; state_out[1] = (int64_t)h; state_out[2] = sk.n; }
     if (!rc && !sk.err && stop) {
-        /* flush :185-194 */
+        /* flush :193-202 */
         while (l > 0 || h + 1 < denom) {
             i128 b = fdiv(l, decision);
             if (region_overlap(l, h, b * decision, (b + 1) * decision) <
@@ -245,7 +245,7 @@ int orc_ac_encode(int prec, const int64_t *dist, int64_t stride, int64_t ntab, c
 }
 
 /* ------------------------------------------------------------------ */
-/* A_from_bin (arith_code.py:233-345): literal bit-at-a-time decoder,   */
+/* A_from_bin (arith_code.py:248-334): literal bit-at-a-time decoder,   */
 /* including its flush() heuristic (extra trailing symbols).            */
 /* ------------------------------------------------------------------ */
 typedef struct {
@@ -323,7 +323,7 @@ static int afb_flush(afb *d) {
 }
 
 /*
- * == list(A_from_bin(...).run(bits, stop))  (arith_code.py:336-340).
+ * == list(A_from_bin(...).run(bits, stop))  (arith_code.py:322-326).
  * max_syms > 0 stops (ORC_OK) once that many symbols are out: the reference has no
  * length framing, its decoder keeps emitting while the bit window allows.
  */
@@ -379,7 +379,7 @@ static void rg_step(region *r, i128 l, i128 h, i128 d, bitsink *sk) {
 }
 
 /*
- * Compress path of ACSampler.sample_scaled_cdf (arithmetic_coding.py:73-93) driven
+ * Compress path of ACSampler.sample_scaled_cdf (arithmetic_coding.py:73-95) driven
  * over n tokens, then flush_compress (:52-58).  cdf: inclusive cumulative tables
  * (uint64 in the reference: cumsum(...).astype(np.uint64)), denom = cdf[-1].
  * bits == everything the reference hands to compress_output.
@@ -403,7 +403,7 @@ int orc_acs_encode(int prec, const uint64_t *cdf, int64_t stride, int64_t ntab, 
 }
 
 /*
- * Expand path of ACSampler.sample_scaled_cdf (arithmetic_coding.py:94-127), LITERALLY,
+ * Expand path of ACSampler.sample_scaled_cdf (arithmetic_coding.py:96-124), LITERALLY,
  * with exact integers (the reference multiplies a Python int by np.uint64, which
  * overflows silently under numpy 2; goldens are made with object-dtype cdfs).  Includes
  * the reference's bisect_left / d=one quirks (:96), so it does NOT always round-trip.

@@ -18,12 +18,12 @@ _SO = os.path.join(_HERE, "_build", "liblac_oracle.so")
 ERRORS = {
     -1: "bad argument",
     -2: "output buffer too small",
-    -3: "unknown symbol (arith_code.py:105)",
-    -4: "predictor range does not correspond to val (arith_code.py:283)",
+    -3: "unknown symbol (arith_code.py:100-101)",
+    -4: "predictor range does not correspond to val (arith_code.py:277-278)",
     -5: "carry out of first bit",
-    -6: "max() of empty range (arith_code.py:324)",
-    -7: "ZeroDivisionError (arith_code.py:319)",
-    -8: "IndexError in ACSampler lookup (arithmetic_coding.py:108)",
+    -6: "max() of empty range (arith_code.py:312)",
+    -7: "ZeroDivisionError (arith_code.py:305-307)",
+    -8: "IndexError in ACSampler lookup (arithmetic_coding.py:114-115)",
 }
 
 
@@ -82,7 +82,7 @@ def _ptr(a):
 
 
 class _Uniform:
-    """Stands for the reference's uniform base class Predictor(n) (arith_code.py:63-74)."""
+    """Stands for the reference's uniform base class Predictor(n) (arith_code.py:64-74)."""
 
     def __init__(self, n):
         self.n = int(n)

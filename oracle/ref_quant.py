@@ -5,7 +5,7 @@ them with the same numpy reproduces the reference's tables exactly.
 
   calc_dist     llama_compress.py:24-30  (Llama_AC.calc_dist)
   llama_minp    llama_compress.py:43-45  (Llama_AC.minp)
-  acs_cdf       arithmetic_coding.py:59-72 (ACSampler.sample + get_lop_bias)
+  acs_cdf       arithmetic_coding.py:57-72 (ACSampler.sample + get_lop_bias)
 """
 import numpy as np
 

@@ -265,7 +265,7 @@ def gen_acs(rng):
                 toks = [int(rng.choice(V, p=p)) for p in pdfs]
                 cdfs = []
                 for p in pdfs:
-                    # ACSampler.sample's own expressions (arithmetic_coding.py:59-63), kept exact as ints
+                    # ACSampler.sample's own expressions (arithmetic_coding.py:58-61), kept exact as ints
                     smp = acs.ACSampler(prec)
                     q = np.array(p, dtype=np.float64)
                     q += smp.get_lop_bias(q)

@@ -100,7 +100,7 @@ def test_multi_part_encode_decode_roundtrip(V, S, T):
 @pytest.mark.parametrize("V,S", [(32000, 60), (65536, 40), (131072, 24)])
 def test_streams_ending_inside_the_first_bit_window(V, S):
     """Streams of 15..22 bytes end inside the 16 bytes the decoder loads at stream start: the bytes past the end
-    must read as zeros (A_from_bin pads with zeros, arith_code.py:262-266) and the in-range bytes next to them
+    must read as zeros (A_from_bin sees no further bits, arith_code.py:322-326) and the in-range bytes next to them
     must not be disturbed.  (Regression: a predicated byte gather was once miscompiled for exactly this case.)"""
     for T, scale in ((5, 6.0), (5, 8.0), (6, 4.0)):
         rng = np.random.default_rng(V + T)
@@ -360,7 +360,7 @@ def test_capacity_overflow_never_writes_outside_the_stream_region():
 
 def test_bad_symbol_reaches_the_stream_status():
     """A symbol outside [0, V) must not be coded as nothing: the reference raises 'unknown symbol'
-    (arith_code.py:104-105)."""
+    (arith_code.py:100-101)."""
     rng = np.random.default_rng(42)
     S, T, V = 3, 5, 100
     logits = _dev(rng.standard_normal((S, T, V)).astype(np.float32))

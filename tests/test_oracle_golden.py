@@ -117,7 +117,7 @@ def test_pack_unpack_roundtrip():
 
 
 def test_ac_uniform_predictor(golden_dir):
-    """AC(Predictor(n), prec): the reference's uniform, floor-mapped base class (arith_code.py:63-74); its
+    """AC(Predictor(n), prec): the reference's uniform, floor-mapped base class (arith_code.py:64-74); its
     default coder AC() is AC(Predictor(3), 16).  Encoder bit-exact, literal decoder identical including the
     junk symbols its flush() appends (negative ones too), value-based decode returns the coded symbols."""
     g = _load(golden_dir, "ac_uniform.npz")
