@@ -24,7 +24,6 @@
 #include <climits>
 #include <cstdint>
 #include <cstdlib>
-#include <mutex>
 #include <cuda_runtime.h>
 
 #include "launch.h"
@@ -34,9 +33,6 @@
 
 #ifndef LAC_DEFAULT_TILE_WARPS
 #define LAC_DEFAULT_TILE_WARPS 32
-#endif
-#ifndef LAC_SUMMARY_REGS
-#define LAC_SUMMARY_REGS 48
 #endif
 
 namespace lac {
@@ -225,11 +221,8 @@ struct TileEngine {
     }
 };
 
-// 48 registers (no spills) instead of the 64 a 1024-thread block could have: the pass is bandwidth-bound either way,
-// and the 16 K registers per SM this leaves free let the small second-pass kernels of the previous sub-slice run
-// next to it (launch.h: Side).
 template <int VEC, bool TMA, int NCH, int TW>
-__global__ void __maxnreg__(LAC_SUMMARY_REGS)
+__global__ void __launch_bounds__(32 * TW, 32 / TW)
 summary_kernel(const __grid_constant__ SumParams sp, uint64_t* __restrict__ summ) {
     using Eng = TileEngine<VEC, TMA, NCH, TW>;
     if (TMA) Eng::setup();
@@ -412,61 +405,6 @@ int64_t summ_rows_for(int64_t want, int parts, const void* ws, size_t ws_bytes) 
     return chunk > want ? want : chunk;
 }
 
-// ------------------------------------------------------------------ side stream (pipelined sub-slices)
-namespace {
-struct SideSlot {
-    std::mutex mu;
-    Side side;
-    int state = 0;  // 0: not created, 1: ready, -1: failed
-};
-SideSlot g_side[64];
-}  // namespace
-
-Side* side_acquire(cudaStream_t caller) {
-    static const bool off = getenv("LAC_NO_PIPELINE") != nullptr;
-    if (off) return nullptr;
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(caller, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
-        cudaGetLastError();
-        return nullptr;
-    }
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    SideSlot& sl = g_side[dev];
-    sl.mu.lock();
-    if (sl.state == 0) {
-        bool ok = cudaStreamCreateWithFlags(&sl.side.st, cudaStreamNonBlocking) == cudaSuccess;
-        cudaEvent_t* evs[5] = {&sl.side.ev_start, &sl.side.ev_sum[0], &sl.side.ev_sum[1], &sl.side.ev_done[0],
-                               &sl.side.ev_done[1]};
-        for (cudaEvent_t* e : evs) ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
-        sl.state = ok ? 1 : -1;
-        if (!ok) cudaGetLastError();
-    }
-    if (sl.state != 1) {
-        sl.mu.unlock();
-        return nullptr;
-    }
-    return &sl.side;
-}
-void side_release(Side* s) {
-    for (SideSlot& sl : g_side)
-        if (&sl.side == s) {
-            sl.mu.unlock();
-            return;
-        }
-}
-
-// Sub-slices of a quarter of the call (at least 2 tokens' worth of work per sub-slice is not required: 1 token is
-// fine), two summary buffers in the scratch.  Only calls that stream at least 64 MB of logits are pipelined.
-int64_t pipeline_tokens(int64_t n, int64_t T, int V, int parts, const void* ws, size_t ws_bytes) {
-    if (T < 2 || n < 1) return 0;
-    if ((double)n * (double)T * (double)V * 4.0 < 64.0 * 1048576.0) return 0;
-    int64_t tc = (T + 3) / 4;
-    const int64_t fit = summ_rows_for(n * T, parts, ws, ws_bytes) / (2 * n);  // two buffers
-    if (fit < 1) return 0;
-    return tc < fit ? tc : fit;
-}
-
 // Scratch: the caller's workspace when it is large enough, else a stream-ordered allocation (cudaMallocAsync; the
 // default pool's release threshold is raised once so repeated calls do not go back to the OS).
 cudaError_t scratch_get(Scratch* sc, size_t bytes, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -499,12 +437,12 @@ cudaError_t launch_pairs_status(const float* logits, int64_t n, int64_t T, int64
                                 uint32_t* pairs, uint32_t* status, cudaStream_t st) {
     const int64_t rows = n * T;
     if (rows == 0) return cudaSuccess;
-    const unsigned blocks = (unsigned)((rows + 3) / 4);  // 4 warps per block: fits next to a resident summary CTA
+    const unsigned blocks = (unsigned)((rows + 7) / 8);
 #define LAC_PAIR(CL_)                                                                                                 \
     if (path == 0)                                                                                                    \
-        pair_kernel<1, CL_><<<blocks, 128, 0, st>>>(logits, rows, T, so, st_, V, summ, syms, sym_stride, pairs, status); \
+        pair_kernel<1, CL_><<<blocks, 256, 0, st>>>(logits, rows, T, so, st_, V, summ, syms, sym_stride, pairs, status); \
     else                                                                                                              \
-        pair_kernel<4, CL_><<<blocks, 128, 0, st>>>(logits, rows, T, so, st_, V, summ, syms, sym_stride, pairs, status)
+        pair_kernel<4, CL_><<<blocks, 256, 0, st>>>(logits, rows, T, so, st_, V, summ, syms, sym_stride, pairs, status)
     LAC_BY_PARTS(parts, LAC_PAIR)
 #undef LAC_PAIR
     return cudaGetLastError();

@@ -680,48 +680,10 @@ cudaError_t launch_encode_logits(const float* logits, int64_t n, int64_t T, int6
     int parts = 1;
     const int path = path_for(logits, V, ss, ts, &parts);
     if (path < 0) return cudaErrorInvalidValue;
-    const bool fused = T <= 4;
-    // ---- long slices: pipelined sub-slices (pass 1 of h + 1 on the caller's stream, pair + coder of h on the side
-    // stream, two scratch buffers), only the last sub-slice's second passes are exposed
-    const int64_t tp = fused ? 0 : pipeline_tokens(n, T, V, parts, ws, ws_bytes);
-    Side* side = tp > 0 ? side_acquire(st) : nullptr;
-    if (side) {
-        Scratch sc;
-        const size_t half = summ_bytes(n * tp, parts);
-        cudaError_t e = scratch_get(&sc, 2 * half, ws, ws_bytes, st);
-        if (e == cudaSuccess) e = cudaEventRecord(side->ev_start, st);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(side->st, side->ev_start, 0);
-        int h = 0, last = -1;
-        for (int64_t t0 = 0; t0 < T && e == cudaSuccess; t0 += tp, h++) {
-            const int64_t tn = T - t0 < tp ? T - t0 : tp;
-            const int b = h & 1;
-            char* buf = (char*)sc.p + (size_t)b * half;
-            uint32_t* pairs = (uint32_t*)(buf + summ_only_bytes(n * tp, parts));
-            const float* base = logits + t0 * ts;
-            if (h >= 2) e = cudaStreamWaitEvent(st, side->ev_done[b], 0);
-            if (e == cudaSuccess) e = launch_summary(base, n, tn, ss, ts, V, parts, path, 0, (uint64_t*)buf, st);
-            if (e == cudaSuccess) e = cudaEventRecord(side->ev_sum[b], st);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(side->st, side->ev_sum[b], 0);
-            if (e == cudaSuccess)
-                e = launch_pairs(base, n, tn, ss, ts, V, parts, path, (const uint64_t*)buf, syms + t0, sym_stride, pairs,
-                                 side->st);
-            if (e == cudaSuccess)
-                e = launch_encode_pairs_at(pairs, n, tn, tn, 1, ntok, t0, state, out, out_stride,
-                                           (finish && t0 + tn >= T) ? 1 : 0, P, side->st);
-            if (e == cudaSuccess) e = cudaEventRecord(side->ev_done[b], side->st);
-            last = b;
-        }
-        if (last >= 0) {
-            const cudaError_t ej = cudaStreamWaitEvent(st, side->ev_done[last], 0);
-            if (e == cudaSuccess) e = ej;
-        }
-        side_release(side);
-        const cudaError_t ef = scratch_put(&sc, st);
-        return e != cudaSuccess ? e : ef;
-    }
     const int64_t Tn = T < 1 ? 1 : T;
     int64_t tc = summ_rows_for(n * Tn, parts, ws, ws_bytes) / n;
     tc = tc < 1 ? 1 : (tc > Tn ? Tn : tc);
+    const bool fused = T <= 4;
     Scratch sc;
     cudaError_t e = scratch_get(&sc, summ_bytes(n * tc, parts), ws, ws_bytes, st);
     if (e != cudaSuccess) return e;

@@ -59,7 +59,7 @@ __device__ __forceinline__ int tokens_of(const SerialParams& p, int64_t s) {
 }
 
 template <int VEC, int CL>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(128, 1)
 decode_serial_kernel(const __grid_constant__ SerialParams rp, int V, const uint64_t* __restrict__ summ,
                      lac_dec_state* __restrict__ state, const uint8_t* __restrict__ bytes,
                      const int64_t* __restrict__ offsets, int32_t* __restrict__ syms, int64_t sym_stride, int P) {
@@ -242,24 +242,7 @@ __global__ void dec_init_kernel(lac_dec_state* state, int64_t n, int P, const ui
     state[s]._pad = 0;
 }
 
-// Decode = summary pass + serial pass per token chunk.  Calls that stream >= 64 MB of logits are cut into (about)
-// four sub-slices: the summary pass of sub-slice h + 1 runs on the caller's stream while the serial pass of
-// sub-slice h runs on the side stream (two summary buffers), so only the last serial pass is exposed.
-static cudaError_t launch_serial(const SerialParams& rp, int V, int parts, int path, const uint64_t* summ,
-                                 lac_dec_state* state, const uint8_t* bytes, const int64_t* offsets, int32_t* syms,
-                                 int64_t sym_stride, int P, cudaStream_t st) {
-    // 2 warps per block: a block (2 x 147 registers x 32) fits into the registers a resident summary CTA leaves free
-    const unsigned blocks = (unsigned)((rp.n_streams + 1) / 2);
-#define LAC_SERIAL(CL_)                                                                                          \
-    if (path == 0)                                                                                               \
-        decode_serial_kernel<1, CL_><<<blocks, 64, 0, st>>>(rp, V, summ, state, bytes, offsets, syms, sym_stride, P); \
-    else                                                                                                         \
-        decode_serial_kernel<4, CL_><<<blocks, 64, 0, st>>>(rp, V, summ, state, bytes, offsets, syms, sym_stride, P)
-    LAC_BY_PARTS(parts, LAC_SERIAL)
-#undef LAC_SERIAL
-    return cudaGetLastError();
-}
-
+// Decode = summary pass + serial pass per token chunk (~240k rows of a 32000-element vocabulary per chunk).
 cudaError_t launch_decode(const float* logits, int64_t n_streams, int64_t T, int64_t stream_stride,
                           int64_t tok_stride, int V, const int32_t* ntok, lac_dec_state* state,
                           const uint8_t* bytes, const int64_t* offsets, int32_t* syms, int64_t sym_stride,
@@ -268,52 +251,29 @@ cudaError_t launch_decode(const float* logits, int64_t n_streams, int64_t T, int
     int parts = 1;
     const int path = path_for(logits, V, stream_stride, tok_stride, &parts);
     if (path < 0) return cudaErrorInvalidValue;
-    const int64_t tp = pipeline_tokens(n_streams, T, V, parts, ws, ws_bytes);
-    Side* side = tp > 0 ? side_acquire(st) : nullptr;
-    Scratch sc;
-    cudaError_t e;
-    if (side) {
-        const size_t half = summ_bytes(n_streams * tp, parts);
-        e = scratch_get(&sc, 2 * half, ws, ws_bytes, st);
-        if (e == cudaSuccess) e = cudaEventRecord(side->ev_start, st);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(side->st, side->ev_start, 0);  // coder state, earlier work
-        int h = 0, last = -1;
-        for (int64_t t0 = 0; t0 < T && e == cudaSuccess; t0 += tp, h++) {
-            const int64_t tn = T - t0 < tp ? T - t0 : tp;
-            const int b = h & 1;
-            uint64_t* summ = (uint64_t*)((char*)sc.p + (size_t)b * half);
-            const float* base = logits + t0 * tok_stride;
-            if (h >= 2) e = cudaStreamWaitEvent(st, side->ev_done[b], 0);  // the serial pass that read this buffer
-            if (e == cudaSuccess) e = launch_summary(base, n_streams, tn, stream_stride, tok_stride, V, parts, path, 0, summ, st);
-            if (e == cudaSuccess) e = cudaEventRecord(side->ev_sum[b], st);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(side->st, side->ev_sum[b], 0);
-            const SerialParams rp{base, n_streams, tn, stream_stride, tok_stride, ntok, t0};
-            if (e == cudaSuccess)
-                e = launch_serial(rp, V, parts, path, summ, state, bytes, offsets, syms + t0, sym_stride, P, side->st);
-            if (e == cudaSuccess) e = cudaEventRecord(side->ev_done[b], side->st);
-            last = b;
-        }
-        // join: everything the side stream did is ordered before whatever follows on the caller's stream
-        if (last >= 0) {
-            const cudaError_t ej = cudaStreamWaitEvent(st, side->ev_done[last], 0);
-            if (e == cudaSuccess) e = ej;
-        }
-        side_release(side);
-        const cudaError_t ef = scratch_put(&sc, st);
-        return e != cudaSuccess ? e : ef;
-    }
     int64_t tc = summ_rows_for(n_streams * T, parts, ws, ws_bytes) / n_streams;
     tc = tc < 1 ? 1 : (tc > T ? T : tc);
-    e = scratch_get(&sc, summ_bytes(n_streams * tc, parts), ws, ws_bytes, st);
+    Scratch sc;
+    cudaError_t e = scratch_get(&sc, summ_bytes(n_streams * tc, parts), ws, ws_bytes, st);
     if (e != cudaSuccess) return e;
     uint64_t* summ = (uint64_t*)sc.p;
+    const unsigned serial_blocks = (unsigned)((n_streams + 3) / 4);
     for (int64_t t0 = 0; t0 < T && e == cudaSuccess; t0 += tc) {
         const int64_t tn = T - t0 < tc ? T - t0 : tc;
         const float* base = logits + t0 * tok_stride;
         e = launch_summary(base, n_streams, tn, stream_stride, tok_stride, V, parts, path, 0, summ, st);
         if (e != cudaSuccess) break;
         const SerialParams rp{base, n_streams, tn, stream_stride, tok_stride, ntok, t0};
-        e = launch_serial(rp, V, parts, path, summ, state, bytes, offsets, syms + t0, sym_stride, P, st);
+#define LAC_SERIAL(CL_)                                                                                             \
+    if (path == 0)                                                                                                  \
+        decode_serial_kernel<1, CL_><<<serial_blocks, 128, 0, st>>>(rp, V, summ, state, bytes, offsets, syms + t0,   \
+                                                                    sym_stride, P);                                 \
+    else                                                                                                            \
+        decode_serial_kernel<4, CL_><<<serial_blocks, 128, 0, st>>>(rp, V, summ, state, bytes, offsets, syms + t0,   \
+                                                                    sym_stride, P)
+        LAC_BY_PARTS(parts, LAC_SERIAL)
+#undef LAC_SERIAL
+        e = cudaGetLastError();
     }
     const cudaError_t ef = scratch_put(&sc, st);
     return e != cudaSuccess ? e : ef;

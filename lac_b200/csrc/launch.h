@@ -16,20 +16,6 @@ struct Scratch {
 cudaError_t scratch_get(Scratch* sc, size_t bytes, void* ws, size_t ws_bytes, cudaStream_t st);
 cudaError_t scratch_put(Scratch* sc, cudaStream_t st);
 
-// Second passes of sub-slice h run on an internal per-device side stream while pass 1 of sub-slice h + 1 runs on the
-// caller's stream (the summary kernel is built for 48 registers so that 16 K registers per SM stay free for them);
-// the caller's stream joins the side stream before the call returns, so the call's stream semantics are unchanged.
-struct Side {
-    cudaStream_t st;
-    cudaEvent_t ev_start, ev_sum[2], ev_done[2];
-};
-// nullptr: do not pipeline (LAC_NO_PIPELINE set, the caller's stream is being captured, or creation failed).
-// On success the per-device mutex is held until side_release().
-Side* side_acquire(cudaStream_t caller);
-void side_release(Side* s);
-// sub-slice length for a call of n streams x T tokens: 0 = do not pipeline
-int64_t pipeline_tokens(int64_t n, int64_t T, int V, int parts, const void* ws, size_t ws_bytes);
-
 int sm_count();
 int max_vocab();
 int path_for(const float* p, int V, int64_t s0, int64_t s1, int* parts);
