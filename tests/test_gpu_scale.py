@@ -128,6 +128,29 @@ def test_full_width_state_carry_1024_streams():
     assert 8.0 < float(want_bits.sum()) / (S * T) < 9.6
 
 
+def test_2048_token_streams_in_128_slices_against_the_oracle():
+    """configs[1]'s stream length: 2048-token streams coded as 128 slices of 16 tokens with the coder state carried
+    across 127 call boundaries (as bench.py does at 1024 streams), the bytes of whole streams against the oracle,
+    then decoded slice by slice."""
+    S, V, T, SL = 8, 32000, 2048, 16
+    g = torch.Generator(device="cuda").manual_seed(8)
+    logits = torch.randn((S, T, V), generator=g, device="cuda") * 3.0
+    syms = torch.multinomial(torch.softmax(logits.view(S * T, V), -1), 1, generator=g).view(S, T).to(torch.int32)
+    ws = coder.Workspace(S * SL, V)
+    enc = coder.StreamEncoder(S, capacity_bytes=T * 8 + 64)
+    for t0 in range(0, T, SL):
+        enc.encode_logits(logits[:, t0:t0 + SL].contiguous(), syms[:, t0:t0 + SL].contiguous(),
+                          finish=(t0 + SL >= T), ws=ws)
+    streams, nbits = enc.bitstreams()
+    hl, hs = logits[:2].cpu().numpy(), syms[:2].cpu().numpy()
+    for s in range(2):
+        assert streams[s] == _oracle_stream(hl[s], hs[s])
+    dec = coder.StreamDecoder(streams)
+    back = torch.cat([dec.decode_logits(logits[:, t0:t0 + SL].contiguous(), ws=ws) for t0 in range(0, T, SL)], dim=1)
+    assert torch.equal(back, syms)
+    assert 8.5 < float(nbits.sum()) / (S * T) < 9.2
+
+
 # ------------------------------------------------------------------ configs[4] shape
 def test_8192_streams_vocab_128256_token_steps():
     """The decode-heavy shape: 8192 concurrent streams, vocab 128256, T = 1 per call (4.2 GB of logits per step):
