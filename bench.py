@@ -566,6 +566,10 @@ def run_llama(args):
             "encode_s": t_enc, "decode_s": t_dec, "lossless": True,
             "bits_per_token": float(c.nbits.sum()) / max(n_tokens, 1), "container_bytes": len(blob),
             "step_split": split, "clocks": clk,
+            # this workload IS end to end: host token ids in, LACB bytes out (and back); the logits never leave the GPU
+            "e2e": {"value": n_tokens / (t_enc + t_dec), "unit": UNIT, "h2d_bytes_per_step": 4 * n_tokens + len(blob),
+                    "d2h_bytes_per_step": len(blob) + 4 * n_tokens,
+                    "api": "LlamaCompressor.compress(tokens) -> bytes, LlamaCompressor.decompress(bytes) -> tokens"},
             "collectives": "one all_gather of (tokens, bits) per chunk + one all_gather of the payload per job; none in the coding loop",
         }
         print(json.dumps(line))
