@@ -2,18 +2,20 @@
 """bench.py -- coded tokens/s (encode + decode) of the arithmetic-coding hot path.
 
 Workload (BASELINE.json configs[1]): coder-only sweep, precomputed random fp32 logits, vocab
-32000, 1024 streams x 2048 tokens, encode + decode on one B200.  2048 tokens x 1024 streams of
-fp32 logits are 268 GB, so the job is run as steps of [1024 streams x SLICE tokens]; one step
-= one pass of the hot path over one such batch, every stream slice coded as a self-contained
-chunk (init -> CDF lookup -> range encode -> flush -> init decoder -> fused CDF/search/decode).
-The same logits buffer (2.1 GB, far larger than the 126 MB L2) is read once by the encode
-side and once by the decode side of every step.
+32000, 1024 streams x 2048 tokens, encode + decode on one B200.  One step = the WHOLE job: lac_enc_init once,
+128 slices of [1024 streams x 16 tokens] through lac_ac_encode_logits_f32 with the coder state carried, one flush;
+then lac_dec_init once and 128 slices through lac_ac_decode_logits_f32; the decoded symbols are compared.  The
+268 GB of logits of a whole job do not fit in HBM, so every slice reads the same resident 2.1 GB buffer (far larger
+than the 126 MB L2) with its own symbols.  A second timed block repeats the measurement at vocab 128256 (the
+north-star's target shape) with its own clock record: roofline.v128256.
 
   python bench.py --gpus N --steps K --warmup W           # this repo, device-resident `value` + host `e2e`
   python bench.py --impl reference ...                    # the reference's CPU algorithm (oracle port)
+  python bench.py --workload llama --model 1b|8b ...      # configs[2] / [3]: model in the loop, sharded, one LACB file
+  python bench.py --workload stress                       # configs[4]: 8192 streams x vocab 128256, per-token decode
 
 Under torchrun every rank codes its own 1024 streams (independent chunks shard with no
-data-path collective); the only collective is the gather of per-stream bit lengths.
+data-path collective); the only collective is ONE gather of per-stream bit lengths per job.
 """
 import argparse
 import json

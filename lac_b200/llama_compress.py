@@ -23,7 +23,6 @@ gathered on the device from the token matrix with the device-side position.
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
