@@ -192,3 +192,23 @@ def test_8192_streams_vocab_128256_token_steps():
         sy = np.array([keep_s[t][s] for t in range(steps)], dtype=np.int32)
         assert streams[s] == _oracle_stream(lg, sy)
     print(f"decode step, {S} streams x vocab {V}: {min(ms):.3f} ms = {S * V * 4 / min(ms) / 1e6:.0f} GB/s")
+
+
+# ------------------------------------------------------------------ configs[2] shape (model in the loop)
+def test_llama_path_64_chunks_of_2048_tokens():
+    """The llama_compress path at the stated chunk geometry: 64 full chunks of 2048 tokens plus a ragged one, batches
+    of 32 streams (the last batch padded), the per-token step replayed from CUDA graphs across every attention bucket
+    (128 ... 2048 cache slots), one LACB file, decompressed and compared.  The predictor is the `tiny` preset (the
+    1.1 B preset runs the same code in bench.py --workload llama)."""
+    from lac_b200 import container, llama_compress as lc
+    chunk, B = 2048, 32
+    cfg = lc.CONFIGS["tiny"]
+    model = lc.LlamaModel(cfg, n_streams=B, max_len=chunk, seed=1)
+    comp = lc.LlamaCompressor(model, chunk_tokens=chunk)
+    rng = np.random.default_rng(9)
+    toks = rng.integers(0, cfg.vocab, 64 * chunk + 777).astype(np.int32)
+    blob = comp.compress(toks)
+    c = container.unpack(blob)
+    assert c.n_chunks == 65 and int(c.ntok[-1]) == 777 and c.batch_streams == B and c.chunk_tokens == chunk
+    assert np.array_equal(comp.decompress(blob), toks)
+    assert len(comp.engine.graphs) == 2 * 5          # (enc, dec) x buckets 128, 256, 512, 1024, 2048
