@@ -509,6 +509,7 @@ def _step_split(engine, bucket, reps=20):
                 enc.reset()
     torch.cuda.current_stream(dev).wait_stream(st)
     torch.cuda.synchronize()
+    enc.reset()   # the replays above coded the same token over and over: start from clean streams
     res["coder_share_of_encode_step"] = max(0.0, 1.0 - res["model_ms"] / res["encode_step_ms"])
     res["bucket"] = bucket
     return res

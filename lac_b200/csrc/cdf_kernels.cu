@@ -259,8 +259,10 @@ pair_kernel(const float* __restrict__ logits, int64_t rows, int64_t T, int64_t s
 
 // ------------------------------------------------------------------ TABLE (second pass of lac_cdf_build_f32)
 // Full exclusive cumulative table: one warp per segment.  The logits are read a second time (from L2: the
-// launcher keeps the row chunk small enough), the table is written once.
-template <int CL>
+// launcher keeps the row chunk small enough), the table is written once.  VEC = 4: slab k of the segment is the 32
+// consecutive float4 groups g0 + 32 k + lane -- 512-byte coalesced loads and stores, one warp scan of the group sums
+// per slab.  VEC = 1 (unaligned rows / V % 4 != 0): lane l walks 32 consecutive elements after one scan.
+template <int VEC, int CL>
 __global__ void __launch_bounds__(256)
 table_kernel(const float* __restrict__ logits, int64_t rows, int64_t row_stride, int V,
              const uint64_t* __restrict__ summ, uint32_t* __restrict__ cum) {
@@ -271,7 +273,8 @@ table_kernel(const float* __restrict__ logits, int64_t rows, int64_t row_stride,
     const int64_t r = unit / NW;
     const int gw = (int)(unit - r * NW);
     const int G = lq::groups_of(V);
-    const int e0 = 4 * lq::seg_group<CL>(gw, G), e1 = min(V, 4 * lq::seg_group<CL>(gw + 1, G));
+    const int gb = lq::seg_group<CL>(gw, G), ge = lq::seg_group<CL>(gw + 1, G);
+    const int e0 = 4 * gb, e1 = min(V, 4 * ge);
     if (e0 >= e1) return;
     RowSum<CL> rs;
     rs.load(summ + r * NW, lane);
@@ -284,6 +287,39 @@ table_kernel(const float* __restrict__ logits, int64_t rows, int64_t row_stride,
     const uint32_t nref = lq::nref_of_code(code);
     const float* row = logits + r * row_stride;
     uint32_t* out = cum + r * (int64_t)V;
+    if (VEC == 4) {
+        const bool out16 = (((uintptr_t)out) & 15) == 0;
+        uint64_t c0 = 0;  // in-segment prefix at the start of the slab
+#pragma unroll 1
+        for (int k = 0; k < kPerThread / 4; k++) {
+            if (gb + 32 * k >= ge) break;  // warp-uniform
+            const int g = gb + 32 * k + lane;
+            const bool in = g < ge;
+            const float4 x = __ldg(reinterpret_cast<const float4*>(row) + (in ? g : ge - 1));
+            uint32_t q[4];
+            q_of2(x.x, x.y, nref, q[0], q[1]);
+            q_of2(x.z, x.w, nref, q[2], q[3]);
+            const uint64_t gs = in ? (uint64_t)q[0] + q[1] + (uint64_t)q[2] + q[3] : 0ull;
+            const uint64_t inc = warp_incl_scan(gs, lane);
+            uint64_t c = c0 + inc - gs;
+            c0 += __shfl_sync(0xffffffffu, inc, 31);
+            if (in) {
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    o[e] = lq::cum_of(front + lq::shr64(c, d), (uint32_t)(4 * g + e), sc);
+                    c += q[e];
+                }
+                if (out16) {
+                    *reinterpret_cast<uint4*>(out + 4 * (int64_t)g) = make_uint4(o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; e++) out[4 * (int64_t)g + e] = o[e];
+                }
+            }
+        }
+        return;
+    }
     // lane l takes the 32 consecutive elements e0 + 32 l ...: one scan of the lane totals, then a serial walk
     const int b = e0 + 32 * lane;
     uint32_t q[kPerThread];
@@ -500,7 +536,9 @@ cudaError_t launch_build(const float* logits, int64_t rows, int V, int64_t row_s
         e = launch_summary(base, rn, 1, row_stride, 0, V, parts, path, 1, summ, st);
         if (e != cudaSuccess) break;
         const unsigned blocks = (unsigned)((rn * 32 * parts + 7) / 8);
-#define LAC_TABLE(CL_) table_kernel<CL_><<<blocks, 256, 0, st>>>(base, rn, row_stride, V, summ, cum + r0 * (int64_t)V)
+#define LAC_TABLE(CL_)                                                                                          \
+    if (path == 0) table_kernel<1, CL_><<<blocks, 256, 0, st>>>(base, rn, row_stride, V, summ, cum + r0 * (int64_t)V); \
+    else table_kernel<4, CL_><<<blocks, 256, 0, st>>>(base, rn, row_stride, V, summ, cum + r0 * (int64_t)V)
         LAC_BY_PARTS(parts, LAC_TABLE)
 #undef LAC_TABLE
         e = cudaGetLastError();

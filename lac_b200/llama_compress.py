@@ -218,14 +218,19 @@ class StepEngine:
         cur.wait_stream(self.stream)
 
     def _snapshot(self, kind):
+        """Everything a step changes that the next step reads: position, coder state, decoded tokens, and -- encode
+        side -- the stream bytes (a carry ripples into bytes already written, so a repeated step would add it twice)."""
         st = self.enc.state if kind == "enc" else self.dec.state
-        return (self.m.pos.clone(), st.clone(), self.tok.clone())
+        out = self.enc.out.clone() if kind == "enc" else None
+        return (self.m.pos.clone(), st.clone(), self.tok.clone(), out)
 
     def _restore(self, kind, snap):
         st = self.enc.state if kind == "enc" else self.dec.state
         self.m.pos.copy_(snap[0])
         st.copy_(snap[1])
         self.tok.copy_(snap[2])
+        if snap[3] is not None:
+            self.enc.out.copy_(snap[3])
 
     # ---- whole batches
     def encode_batch(self, tokens: np.ndarray, ntok: np.ndarray):
