@@ -134,3 +134,30 @@ def test_ac_uniform_predictor(golden_dir):
         assert (rc != 0) == (err != ""), (nm, err, rc)
         if stop:
             assert np.array_equal(orc.ac_decode_n(orc.uniform(n), bits, len(syms), prec=prec), syms), nm
+
+
+def test_api_traces_bits_and_encoder_state(golden_dir):
+    """tests/golden/api_traces.npz (call-by-call traces of the reference's incremental API): the oracle produces the
+    same carry-resolved bits, the same (l, h, emitted_bits) before the flush, and the value-based decoder the same
+    symbols -- for fixed tables (incl. the fudged_dist branch), the uniform base class and the adaptive model."""
+    g = _load(golden_dir, "api_traces.npz")
+    for nm in g["names"]:
+        kind, prec, V = str(g[f"{nm}/kind"]), int(g[f"{nm}/prec"]), int(g[f"{nm}/V"])
+        syms, want = g[f"{nm}/syms"], g[f"{nm}/bits"]
+        if kind == "cdf":
+            tabs = g[f"{nm}/dist"]
+        elif kind == "uniform":
+            tabs = orc.uniform(V)
+        else:
+            tabs = _adaptive_tables(syms, V)[: len(syms)]
+        bits, st = orc.ac_encode(tabs, syms, prec=prec, stop=1, return_state=True)
+        assert np.array_equal(bits, want), nm
+        l, h, nb, _ = g[f"{nm}/enc_states"][len(syms) - 1]        # state after the last symbol, before the flush
+        assert (int(st[0]), int(st[1]), int(st[2])) == (int(l), int(h), int(nb)), nm
+        # the digits the reference yields call by call, summed with carries, are those bits
+        flat = g[f"{nm}/digits"]
+        r = 0
+        for d in flat:
+            r = (r << 1) + int(d)
+        assert r == int("0" + "".join(map(str, want.tolist())), 2) and len(flat) == len(want), nm
+        assert np.array_equal(orc.ac_decode_n(tabs, want, len(syms), prec=prec), syms), nm
