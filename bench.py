@@ -179,6 +179,26 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------ GPU legs
+def pin_to_gpu_numa_node(gpu_index):
+    """Run this rank on the CPU cores next to its GPU (NVML's affinity mask), so that the pinned host buffers of the
+    e2e leg are first-touched on that GPU's NUMA node: with several ranks per box the host-to-device copies otherwise
+    cross the socket interconnect.  Best effort; returns the number of cores or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 class Job:
     """One full coder job on one GPU: S streams x CHUNK tokens coded as CHUNK / SLICE slices with the coder state
     carried from slice to slice (lac_enc_init once, finish once, lac_dec_init once).  The logits of a full job
@@ -272,6 +292,7 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cores = pin_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -395,7 +416,7 @@ def run_gpu(args):
         e2e = {"value": world * rows * e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": e_steps, "ms_per_step": dt / e_steps * 1e3,
                "step": f"one [{S} x {T}] slice of the job, host logits in, host bytes / symbols out",
-               "bound": "pcie", "h2d_gbps": h2d * e_steps / dt / 1e9,
+               "bound": "pcie", "h2d_gbps": h2d * e_steps / dt / 1e9, "cores_near_gpu": numa_cores,
                "api": "lac_encode_logits_host + lac_decode_logits_host (pinned host logits in, host bytes/symbols out)"}
 
     if rank == 0:
