@@ -143,10 +143,10 @@ def test_caller_workspace_gives_the_same_result_and_small_workspaces_chunk():
 
 def test_fused_encoder_equals_lookup_plus_pairs_coder():
     """lac_ac_encode_logits_f32 (one fused kernel) against lac_cdf_lookup_f32 + lac_ac_encode_pairs, all slice
-    shapes the launcher distinguishes (T = 1, 2, 5, 16, 40), ragged streams, state carried across calls."""
+    shapes the launcher distinguishes (T = 1 ... 5, 16, 40), ragged streams, state carried across calls."""
     rng = np.random.default_rng(78)
     S, V = 37, 1000
-    for T in (1, 2, 5, 16, 40):
+    for T in (1, 2, 3, 4, 5, 16, 40):
         logits = (rng.standard_normal((S, T, V)) * 5).astype(np.float32)
         syms = rng.integers(0, V, (S, T)).astype(np.int32)
         ntok = rng.integers(0, T + 1, S).astype(np.int32)
