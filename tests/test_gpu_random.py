@@ -104,3 +104,62 @@ def test_random_shapes_strides_and_alignments(seed):
         cum = torch.empty((T, V), dtype=torch.int32, device="cuda")
         _ffi.check(L.lac_cdf_build_f32(base, T, V, tok_stride, cum.data_ptr(), *wsp, st))
         assert np.array_equal(cum.cpu().numpy().view(np.uint32), orc.lq32_cdf(logits[0])), (seed, V, "build")
+
+
+@pytest.mark.parametrize("V,S,T", [(32000, 5, 1), (32000, 3, 3), (1000, 7, 20), (70001, 2, 4), (128256, 3, 2)])
+def test_nothing_is_written_outside_the_declared_buffers(V, S, T):
+    """Guard bytes around every output of the logits-driven calls -- the workspace beyond its declared size, the
+    bitstream buffers (per-token fused path and slice path), the decoded symbols, the pairs, the table -- stay intact.
+    (compute-sanitizer is not available on the GPU pool; this is the bounds check of our own.)"""
+    rng = np.random.default_rng(V + S + T)
+    L = _ffi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    G = 0xA5
+    logits = torch.from_numpy((rng.standard_normal((S, T, V)) * 4).astype(np.float32)).cuda()
+    syms = torch.from_numpy(rng.integers(0, V, (S, T)).astype(np.int32)).cuda()
+    ws_bytes = int(L.lac_workspace_bytes(S * T, V))
+    ws = torch.full((ws_bytes + 4096,), G, dtype=torch.uint8, device="cuda")
+    cap = T * 8 + 64
+    out = torch.full((S + 2, cap), G, dtype=torch.uint8, device="cuda")
+    enc_state = torch.full((S + 2, _ffi.ENC_STATE_BYTES), G, dtype=torch.uint8, device="cuda")
+    _ffi.check(L.lac_enc_init(enc_state[1:].data_ptr(), S, 48, st))
+    _ffi.check(L.lac_ac_encode_logits_f32(logits.data_ptr(), S, T, T * V, V, V, syms.data_ptr(), T, None,
+                                          enc_state[1:].data_ptr(), out[1:].data_ptr(), cap, 1, 48, ws.data_ptr(),
+                                          ws_bytes, st))
+    torch.cuda.synchronize()
+    assert (ws[ws_bytes:] == G).all(), "workspace overrun (encode)"
+    assert (out[0] == G).all() and (out[S + 1] == G).all(), "bitstream buffer overrun"
+    assert (enc_state[0] == G).all() and (enc_state[S + 1] == G).all(), "encoder state overrun"
+    nbits = enc_state[1:S + 1].cpu().numpy().view(np.int64).reshape(S, 4)[:, 2]
+    host_out = out[1:S + 1].cpu().numpy()
+    for s in range(S):
+        used = (int(nbits[s]) + 7) // 8
+        assert (host_out[s, used:] == G).all(), "bytes written past the stream's end"
+    streams = [host_out[s, : (int(nbits[s]) + 7) // 8].tobytes() for s in range(S)]
+    offs = np.zeros(S + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in streams], out=offs[1:])
+    data = torch.from_numpy(np.frombuffer(b"".join(streams) + b"\0" * 16, dtype=np.uint8).copy()).cuda()
+    d_offs = torch.from_numpy(offs).cuda()
+    dec_state = torch.full((S + 2, _ffi.DEC_STATE_BYTES), G, dtype=torch.uint8, device="cuda")
+    back = torch.full((S + 2, T), -7, dtype=torch.int32, device="cuda")
+    ws.fill_(G)
+    _ffi.check(L.lac_dec_init(dec_state[1:].data_ptr(), S, 48, data.data_ptr(), d_offs.data_ptr(), st))
+    _ffi.check(L.lac_ac_decode_logits_f32(logits.data_ptr(), S, T, T * V, V, V, None, dec_state[1:].data_ptr(),
+                                          data.data_ptr(), d_offs.data_ptr(), back[1:].data_ptr(), T, 48, ws.data_ptr(),
+                                          ws_bytes, st))
+    torch.cuda.synchronize()
+    assert (ws[ws_bytes:] == G).all(), "workspace overrun (decode)"
+    assert torch.equal(back[1:S + 1], syms) and (back[0] == -7).all() and (back[S + 1] == -7).all()
+    assert (dec_state[0] == G).all() and (dec_state[S + 1] == G).all()
+    rows = S * T
+    pairs = torch.full((rows + 2, 2), -7, dtype=torch.int32, device="cuda")
+    ws.fill_(G)
+    _ffi.check(L.lac_cdf_lookup_f32(logits.data_ptr(), rows, V, V, syms.data_ptr(), pairs[1:].data_ptr(), None,
+                                    ws.data_ptr(), ws_bytes, st))
+    cum = torch.full((rows + 2, V), -7, dtype=torch.int32, device="cuda")
+    _ffi.check(L.lac_cdf_build_f32(logits.data_ptr(), rows, V, V, cum[1:].data_ptr(), ws.data_ptr(), ws_bytes, st))
+    torch.cuda.synchronize()
+    assert (ws[ws_bytes:] == G).all(), "workspace overrun (lookup / build)"
+    assert (pairs[0] == -7).all() and (pairs[rows + 1] == -7).all()
+    assert (cum[0] == -7).all() and (cum[rows + 1] == -7).all()
+    assert np.array_equal(cum[1:rows + 1].cpu().numpy().view(np.uint32), orc.lq32_cdf(logits.view(rows, V).cpu().numpy()))
