@@ -1,9 +1,11 @@
 // coder_kernels.cu -- batched multi-stream range coder kernels (north-star part (b)).
 //
-//   encode_pairs_kernel   one thread per stream; (lo, hi) pairs on the fixed total 2^32
-//                         (output of the fused lookup) -> MSB-first bytes.  low / high live
-//                         in registers, the k renormalisation bits of a token are appended
-//                         in one step with carry resolution (coder.cuh).
+//   encode_pairs_staged_kernel   one lane per stream, a few streams per warp; (lo, hi) pairs on the fixed total
+//                         2^32 (output of the lookup) -> MSB-first bytes.  low / high live in registers, the k
+//                         renormalisation bits of a token are appended in one step with carry resolution
+//                         (coder.cuh) into a shared-memory stage that the whole warp flushes.
+//   encode_pairs_kernel   the same coder with one thread per stream and direct byte stores (measurement switch)
+//   encode_fused_kernel   symbol ranges + coder in one launch for the model-in-the-loop step (T <= 4)
 //   ac_tables_*           one warp per stream; int64 inclusive cumulative tables exactly as
 //                         CDFPredictor.dist holds them, including fudged_dist
 //                         (arith_code.py:83-93) evaluated as a parallel prefix-max:
@@ -20,6 +22,10 @@
 #include "coder.cuh"
 #include "launch.h"
 #include "rowsum.cuh"
+
+#ifndef LAC_DEFAULT_CODER_SPB
+#define LAC_DEFAULT_CODER_SPB 4
+#endif
 
 namespace lac {
 
@@ -100,6 +106,96 @@ __global__ void encode_pairs_kernel(const uint2* __restrict__ pairs, int64_t n_s
     state[s].high = h;
     state[s].nbits = bw.nbits;
     state[s].status = bw.status;
+}
+
+// ------------------------------------------------------------------ pairs encoder with warp-aggregated output
+// One warp per `spb` streams (lanes 0 .. spb-1 run A_to_bin, low / high in registers).  The bytes of a batch of 16
+// tokens go to a per-stream shared-memory stage (coder::StagedWriter: carries resolved there); after every batch
+// the WHOLE warp copies the stages to the streams' global buffers -- 32 consecutive bytes of one stream per store
+// instruction instead of one byte per store and lane.
+constexpr int kStagedMaxSpb = 16;
+__global__ void __launch_bounds__(32)
+encode_pairs_staged_kernel(const uint2* __restrict__ pairs, int64_t n_streams, int64_t T, int64_t stream_stride,
+                           int64_t tok_stride, const int32_t* __restrict__ ntok, int64_t t0,
+                           lac_enc_state* __restrict__ state, uint8_t* __restrict__ out, int64_t out_stride,
+                           int finish, int P, int spb) {
+    __shared__ uint8_t s_stage[kStagedMaxSpb][coder::StagedWriter::kStage + 1];
+    __shared__ unsigned long long s_base[kStagedMaxSpb];
+    __shared__ int s_fill[kStagedMaxSpb];
+    const int lane = threadIdx.x;
+    const int64_t s0 = (int64_t)blockIdx.x * spb;
+    const int ns = (int)min((int64_t)spb, n_streams - s0);
+    const bool is_coder = lane < ns;
+    const int64_t s = s0 + lane;
+    int64_t l = 0, h = 0, Ts = 0;
+    coder::StagedWriter bw;
+    const uint2* p = pairs;
+    if (is_coder) {
+        l = state[s].low;
+        h = state[s].high;
+        bw.open(out + s * out_stride, s_stage[lane], (uint64_t)out_stride, state[s].nbits, state[s].status);
+        Ts = T;
+        if (ntok) {
+            Ts = (int64_t)ntok[s] - t0;
+            Ts = Ts < 0 ? 0 : (Ts > T ? T : Ts);
+        }
+        p = pairs + s * stream_stride;
+    }
+    constexpr int kBatch = 8;  // pairs fetched together (independent loads in flight), two fetches per flush
+    bool bad = false;
+    int64_t tb0 = 0;
+    do {
+        const bool last = tb0 + 2 * kBatch >= T;
+        if (is_coder) {
+            for (int64_t tq = tb0; tq < tb0 + 2 * kBatch && tq < Ts && !bad; tq += kBatch) {
+                uint2 pr[kBatch];
+#pragma unroll
+                for (int j = 0; j < kBatch; j++) {
+                    const int64_t t = tq + j < Ts ? tq + j : Ts - 1;
+                    pr[j] = p[t * tok_stride];
+                }
+#pragma unroll
+                for (int j = 0; j < kBatch; j++) {
+                    if (tq + j < Ts && !bad) {
+                        if (pr[j].y != 0 && pr[j].y <= pr[j].x) {
+                            // the lookup's sentinel for a symbol outside [0, V) (the reference raises "unknown symbol",
+                            // arith_code.py:100-101), or a zero-width symbol (the reference would never terminate)
+                            bw.status |= (pr[j].x == 0xFFFFFFFFu && pr[j].y == 0xFFFFFFFFu) ? LAC_ST_SYMBOL : LAC_ST_TABLE;
+                            bad = true;
+                        } else if (bw.status & LAC_ST_CAP) {
+                            bad = true;  // truncated: stop coding this stream
+                        } else {
+                            coder::ac_narrow32(l, h, pr[j].x, pr[j].y);
+                            const int k = coder::renorm_count((uint64_t)(h - l + 1), P);
+                            const int64_t E = coder::renorm_apply(l, h, P, k);
+                            bw.append(E, k);
+                        }
+                    }
+                }
+            }
+            if (last) {
+                if (finish && !(bw.status & (LAC_ST_TABLE | LAC_ST_SYMBOL | LAC_ST_CAP))) coder::ac_flush(l, h, P, bw);
+                bw.close();
+            }
+            s_base[lane] = bw.base;
+            s_fill[lane] = bw.fill + bw.tail;
+        }
+        __syncwarp();
+        for (int si = 0; si < ns; si++) {  // the whole warp moves one stream's staged bytes at a time
+            uint8_t* dst = out + (s0 + si) * out_stride + s_base[si];
+            const int nb = s_fill[si];
+            for (int i = lane; i < nb; i += 32) dst[i] = s_stage[si][i];
+        }
+        __syncwarp();
+        if (is_coder) bw.flushed();
+        tb0 += 2 * kBatch;
+    } while (tb0 < T);
+    if (is_coder) {
+        state[s].low = l;
+        state[s].high = h;
+        state[s].nbits = bw.nbits;
+        state[s].status = bw.status;
+    }
 }
 
 // ------------------------------------------------------------------ fused encoder (second pass of the encode side)
@@ -653,9 +749,18 @@ cudaError_t launch_encode_pairs_at(const uint32_t* pairs, int64_t n, int64_t T, 
                                    const int32_t* ntok, int64_t t0, lac_enc_state* state, uint8_t* out,
                                    int64_t out_stride, int finish, int P, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    // Each thread is a long dependent chain with data-dependent inner loops (bits per token differ per stream),
+    // Each coder lane is a long dependent chain with data-dependent inner loops (bits per token differ per stream),
     // so few streams per warp (less divergence) on many SMs (more schedulers) beat dense blocks.
-    // Measured (1024 streams x 16 tokens): 32 threads per block 22 us, 8: 18 us, 2: 15 us.
+    // Default: the staged kernel, 4 streams per warp, warp-wide flushes (LAC_CODER_SPB=n, 1 .. 16).  Measured per
+    // [1024 x 16] slice inside the encode call: 2 / 4 / 8 streams per warp 0.347 / 0.348 / 0.350 ms, the same as the
+    // thread-per-stream kernel with byte stores (LAC_CODER_SPB=0; LAC_CODER_TPB threads per block, default 2): 0.348 ms.
+    static const int spb_env = getenv("LAC_CODER_SPB") ? atoi(getenv("LAC_CODER_SPB")) : LAC_DEFAULT_CODER_SPB;
+    if (spb_env > 0) {
+        const int spb = spb_env > kStagedMaxSpb ? kStagedMaxSpb : spb_env;
+        encode_pairs_staged_kernel<<<(unsigned)((n + spb - 1) / spb), 32, 0, st>>>(
+            reinterpret_cast<const uint2*>(pairs), n, T, ss, ts, ntok, t0, state, out, out_stride, finish, P, spb);
+        return cudaGetLastError();
+    }
     static const int tpb_env = getenv("LAC_CODER_TPB") ? atoi(getenv("LAC_CODER_TPB")) : 2;
     const int tpb = tpb_env < 1 ? 1 : (tpb_env > 1024 ? 1024 : tpb_env);
     encode_pairs_kernel<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, st>>>(reinterpret_cast<const uint2*>(pairs), n, T, ss,
