@@ -431,7 +431,7 @@ def run_gpu(args):
                          "kernel": "summary_kernel (fused softmax -> fixed-total quantisation -> min-frequency clamp -> "
                                    "segment prefix sums; the one HBM pass over the logits), timed through the whole "
                                    "lac_ac_encode_logits_f32 call, i.e. together with pair_kernel (symbol ranges) and "
-                                   "encode_pairs_kernel (range coder); the ncu launch list under profiles/ gives the split",
+                                   "encode_pairs_staged_kernel (range coder); the ncu launch list under profiles/ gives the split",
                          "achieved": enc_gbs, "peak": peak, "unit": "GB/s", "frac": enc_gbs / peak,
                          "traffic": measured_traffic("summary_kernel", V, rows), "peak_source": peak_src,
                          "peak_note": "the peak is the copy-measured (read + write) figure; a read-only stream reaches 7.2-7.8 TB/s on this part (profiles/microbench/tma_stream_b200.txt), so frac may exceed 1",
