@@ -103,15 +103,20 @@ __device__ __forceinline__ uint2 warp_symbol_range(const float* __restrict__ row
     const uint32_t nref = lq::nref_of_code(code);
     uint64_t part = 0;
     uint32_t qs = 0;
-    // elements of the segment in front of (and including) the symbol: all loads issued together from addresses
-    // clamped to the symbol, masked afterwards
+    // elements of the segment in front of (and including) the symbol: the slabs up to the symbol's (a warp-uniform
+    // count, half of the segment on average), their loads issued together from addresses clamped to the symbol,
+    // masked afterwards
     if (VEC == 4) {
-        const int g0 = lq::seg_group<CL>(gw, G) + lane;
+        const int gbase = lq::seg_group<CL>(gw, G);
+        const int g0 = gbase + lane;
+        const int kmax = (gs - gbase) >> 5;  // slab of the symbol's group
         float4 x[kPerThread / 4];
 #pragma unroll
-        for (int k = 0; k < kPerThread / 4; k++) x[k] = __ldg(reinterpret_cast<const float4*>(row) + min(g0 + 32 * k, gs));
+        for (int k = 0; k < kPerThread / 4; k++)
+            if (k <= kmax) x[k] = __ldg(reinterpret_cast<const float4*>(row) + min(g0 + 32 * k, gs));
 #pragma unroll
         for (int k = 0; k < kPerThread / 4; k++) {
+            if (k > kmax) break;
             const int g = g0 + 32 * k;
             uint32_t q0, q1, q2, q3;
             q_of2(x[k].x, x[k].y, nref, q0, q1);
@@ -121,12 +126,16 @@ __device__ __forceinline__ uint2 warp_symbol_range(const float* __restrict__ row
             if (g == gs) qs = es == 0 ? q0 : es == 1 ? q1 : es == 2 ? q2 : q3;
         }
     } else {
-        const int e0 = 4 * lq::seg_group<CL>(gw, G) + lane;
+        const int ebase = 4 * lq::seg_group<CL>(gw, G);
+        const int e0 = ebase + lane;
+        const int kmax = (sym - ebase) >> 5;
         float x[kPerThread];
 #pragma unroll
-        for (int k = 0; k < kPerThread; k++) x[k] = __ldg(row + min(e0 + 32 * k, sym));
+        for (int k = 0; k < kPerThread; k++)
+            if (k <= kmax) x[k] = __ldg(row + min(e0 + 32 * k, sym));
 #pragma unroll
         for (int k = 0; k < kPerThread; k++) {
+            if (k > kmax) break;
             const int e = e0 + 32 * k;
             const uint32_t q0 = lq::q_of(x[k], nref);
             part += e < sym ? q0 : 0u;
