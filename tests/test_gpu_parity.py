@@ -586,7 +586,7 @@ sys.path.insert(0, sys.argv[1])
 from lac_b200 import coder
 from oracle import oracle as orc
 rng = np.random.default_rng(21)
-for V, S, T in ((32000, 6, 5), (4096, 9, 7), (1000, 4, 6)):
+for V, S, T in ((32000, 6, 5), (4096, 9, 7), (1000, 4, 6), (70004, 3, 20)):
     logits = (rng.standard_normal((S, T, V)) * 5).astype(np.float32)
     syms = rng.integers(0, V, (S, T)).astype(np.int32)
     dl, ds = torch.from_numpy(logits).cuda(), torch.from_numpy(syms).cuda()
@@ -603,16 +603,19 @@ print("ok")
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("env", [{"LAC_NO_TMA": "1"}, {"LAC_TMA_CHUNKS": "2"}, {"LAC_TMA_CHUNKS": "8"}])
+@pytest.mark.parametrize("env", [{"LAC_NO_TMA": "1"}, {"LAC_TMA_CHUNKS": "2"}, {"LAC_TMA_CHUNKS": "8"},
+                                 {"LAC_TILE_WARPS": "16"}, {"LAC_TILE_WARPS": "8"}, {"LAC_CODER_SPB": "0"},
+                                 {"LAC_CODER_SPB": "16"}, {"LAC_CODER_SPB": "0", "LAC_CODER_TPB": "32"}])
 def test_alternative_staging_paths_are_bit_exact(env):
-    """The measurement switches select other instantiations of the row engine (128-bit LDG staging, 2 or 8 TMA
-    chunks per row); they must stay bit-exact with the oracle like the default 4 x 32 KB TMA path."""
+    """The measurement switches select other instantiations of pass 1 (128-bit LDG staging, 2 or 8 TMA chunks per
+    tile, 2 or 4 CTAs per SM) and of the pairs coder (thread-per-stream with byte stores, other streams-per-warp
+    counts); they must stay bit-exact with the oracle like the defaults."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     e = dict(os.environ)
-    for k in ("LAC_NO_TMA", "LAC_TMA_CHUNKS"):
+    for k in ("LAC_NO_TMA", "LAC_TMA_CHUNKS", "LAC_TILE_WARPS", "LAC_CODER_SPB", "LAC_CODER_TPB"):
         e.pop(k, None)
     e.update(env)
     r = subprocess.run([sys.executable, "-c", _PATH_SCRIPT, root], env=e, capture_output=True, text=True, timeout=600)
